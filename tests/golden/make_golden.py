@@ -1,0 +1,303 @@
+"""Generate the golden fixtures in tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference) on seeded inputs, through oracle/ref_shim.py.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+Outputs are small .npz files committed next to this script; the tests (CPU and GPU) read
+only those, never the reference.  torch 2.11.0 / numpy 2.3.5 CPU, torch.set_num_threads(1)
+for run-to-run determinism.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
+sys.path.insert(0, ROOT)
+from oracle import ref_shim  # noqa: E402
+
+ref_shim.install()
+import gym  # noqa: E402  (the stub)
+import torch as th  # noqa: E402
+from icrl.constraint_net import ConstraintNet  # noqa: E402
+from stable_baselines3 import PPOLagrangian  # noqa: E402
+from stable_baselines3.common import logger  # noqa: E402
+from stable_baselines3.common.buffers import RolloutBufferWithCost  # noqa: E402
+from stable_baselines3.common.vec_env import DummyVecEnv  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+REF = ref_shim.REFERENCE_ROOT
+th.set_num_threads(1)
+
+
+def save(name, **arrays):
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"wrote {name}.npz  ({os.path.getsize(path) / 1024:.1f} KB)")
+
+
+def sd_arrays(prefix, state_dict):
+    return {f"{prefix}{k}": v.detach().cpu().numpy().copy() for k, v in state_dict.items()}
+
+
+# ------------------------------------------------------------------------------------------- K1
+
+SHAPES = {
+    # name: obs_dim, acs_dim, is_discrete, cn hidden, policy batch, epochs
+    "lgw": dict(obs_dim=1, acs_dim=2, is_discrete=True, hidden=(20,)),
+    "hc": dict(obs_dim=18, acs_dim=6, is_discrete=False, hidden=(20,)),
+    "ant": dict(obs_dim=113, acs_dim=8, is_discrete=False, hidden=(40, 40)),
+    "point": dict(obs_dim=6, acs_dim=2, is_discrete=False, hidden=(40, 40)),
+}
+
+
+def synth_obs_acs(rng, n, obs_dim, acs_dim, is_discrete, obs_dtype=np.float64):
+    scale = rng.uniform(0.5, 8.0, size=obs_dim)
+    obs = (rng.standard_normal((n, obs_dim)) * scale).astype(obs_dtype)
+    if is_discrete:
+        acs = rng.integers(0, acs_dim, size=(n, 1)).astype(np.float32)
+    else:
+        acs = rng.standard_normal((n, acs_dim)).astype(np.float32)
+    return obs, acs
+
+
+def make_cn(shape, seed, *, normalize=False, clip_obs=20., reg=0.0, no_is=False, per_step=False,
+            expert=None, tkon=-1, tkno=-1, lr=3e-3, obs_select=None, acs_select=None, rng=None):
+    th.manual_seed(seed)
+    s = SHAPES[shape]
+    low = high = None
+    if not s["is_discrete"]:
+        low, high = -np.ones(s["acs_dim"], np.float32), np.ones(s["acs_dim"], np.float32)
+    mean = var = None
+    if normalize:
+        mean = rng.standard_normal(s["obs_dim"])
+        var = rng.uniform(0.3, 9.0, size=s["obs_dim"])
+    eo, ea = expert if expert is not None else (None, None)
+    return ConstraintNet(
+        s["obs_dim"], s["acs_dim"], s["hidden"], None, lambda x: lr, eo, ea, s["is_discrete"], reg,
+        obs_select, acs_select, no_importance_sampling=no_is, per_step_importance_sampling=per_step,
+        clip_obs=clip_obs, initial_obs_mean=mean, initial_obs_var=var, action_low=low, action_high=high,
+        target_kl_old_new=tkon, target_kl_new_old=tkno, eps=1e-5, device="cpu")
+
+
+def golden_k1():
+    rng = np.random.default_rng(1234)
+    for shape in SHAPES:
+        s = SHAPES[shape]
+        for variant, normalize in (("raw", False), ("norm", True)):
+            cn = make_cn(shape, seed=0, normalize=normalize, rng=rng)
+            for dt, tag in ((np.float64, "f64"), (np.float32, "f32")):
+                obs, acs = synth_obs_acs(rng, 257, s["obs_dim"], s["acs_dim"], s["is_discrete"], dt)
+                cost = cn.cost_function(obs, acs)
+                x = cn.prepare_data(obs, acs).numpy()
+                extra = {}
+                if normalize:
+                    extra = dict(obs_mean=cn.current_obs_mean, obs_var=cn.current_obs_var)
+                save(f"k1_{shape}_{variant}_{tag}", obs=obs, acs=acs, cost=cost, x=x, clip_obs=np.float64(20.),
+                     **sd_arrays("p.", cn.network.state_dict()), **extra)
+    # 3-D input as AdjustedRewardCallback passes it (icrl/utils.py:565-567): [T, E, .]
+    cn = make_cn("hc", seed=1, rng=rng)
+    obs, acs = synth_obs_acs(rng, 6 * 5, 18, 6, False, np.float32)
+    obs, acs = obs.reshape(6, 5, 18), acs.reshape(6, 5, 6)
+    save("k1_hc_3d", obs=obs, acs=acs, cost=cn.cost_function(obs, acs), **sd_arrays("p.", cn.network.state_dict()))
+
+    # obs/acs select dims + the real frozen checkpoint shipped with the reference (cpg path)
+    path = os.path.join(REF, "icrl/expert_data/ConstraintTransfer/ICRL/Point/files/best_cn_model.pt")
+    raw = th.load(path)
+    cn = ConstraintNet.load(path, obs_dim=6, acs_dim=2, is_discrete=False, obs_select_dim=[0, 1], acs_select_dim=[-1],
+                            clip_obs=None, obs_mean=None, obs_var=None, action_low=-0.25 * np.ones(2, np.float32),
+                            action_high=0.25 * np.ones(2, np.float32), device="cpu")
+    obs, acs = synth_obs_acs(rng, 300, 6, 2, False, np.float64)
+    obs[:4, :2] = [[0, 0], [5, 5], [-8, 3], [100, -100]]
+    save("k1_point_ckpt", obs=obs, acs=acs, cost=cn.cost_function(obs, acs),
+         loaded_clip_obs_is_none=np.array(cn.clip_obs is None), loaded_action_high_is_none=np.array(cn.action_high is None),
+         hidden_sizes=np.array(raw["hidden_sizes"]), select_dim=np.array(cn.select_dim),
+         **sd_arrays("p.", raw["cn_network"]))
+    path = os.path.join(REF, "icrl/expert_data/ConstraintTransfer/ICRL/AntBroken/files/best_cn_model.pt")
+    raw = th.load(path)
+    cn = ConstraintNet.load(path, obs_dim=113, acs_dim=8, is_discrete=False, device="cpu")
+    obs, acs = synth_obs_acs(rng, 128, 113, 8, False, np.float64)
+    save("k1_antbroken_ckpt", obs=obs, acs=acs, cost=cn.cost_function(obs, acs),
+         hidden_sizes=np.array(raw["hidden_sizes"]), select_dim=np.array(cn.select_dim),
+         **sd_arrays("p.", raw["cn_network"]))
+
+    # a slice of the real AntWall expert rollouts (icrl/icrl.py:25-43 schema)
+    import pickle
+    with open(os.path.join(REF, "icrl/expert_data/AntWall/files/EXPERT/rollouts/0.pkl"), "rb") as f:
+        data = pickle.load(f)
+    cn = make_cn("ant", seed=3, rng=rng)
+    obs, acs = data["observations"][:96], data["actions"][:96]
+    save("k1_ant_expert_slice", obs=obs, acs=acs, cost=cn.cost_function(obs, acs),
+         **sd_arrays("p.", cn.network.state_dict()))
+
+
+# ------------------------------------------------------------------------------------------- K2
+
+def opt_arrays(cn):
+    out = {}
+    st = cn.optimizer.state_dict()["state"]
+    for i, (k, v) in enumerate(sorted(st.items())):
+        out[f"adam.{i}.step"] = np.asarray(float(v["step"]))
+        out[f"adam.{i}.exp_avg"] = v["exp_avg"].numpy().copy()
+        out[f"adam.{i}.exp_avg_sq"] = v["exp_avg_sq"].numpy().copy()
+    return out
+
+
+def golden_k2():
+    rng = np.random.default_rng(99)
+    cases = {
+        # name: shape, episode lengths, n_expert, kwargs, train calls [(iters, lr-progress)]
+        "hc_perstep": ("hc", [500, 500, 400], 900, dict(per_step=True, reg=0.5, tkno=2.5, tkon=10, lr=0.05), 3),
+        "ant_perstep": ("ant", [150, 150], 250, dict(per_step=True, reg=0.6, tkno=2.5, tkon=10, lr=0.005), 3),
+        "hc_perstep_mild": ("hc", [50, 60, 40], 140, dict(per_step=True, reg=0.5, tkno=2.5, tkon=10, lr=0.002), 4),
+        "lgw_perepisode": ("lgw", [40, 35, 50, 25], 160, dict(tkno=10, tkon=10, lr=0.003, clip_obs=20.), 4),
+        "hc_perepisode_norm": ("hc", [30, 20, 25, 40], 100, dict(reg=0.1, lr=0.01, normalize=True), 3),
+        "hc_nois": ("hc", [200, 100], 250, dict(no_is=True, reg=0.5, lr=0.05), 2),
+        "hc_earlystop": ("hc", [60, 50, 40], 120, dict(tkno=1e-4, tkon=10, lr=0.05), 6),
+    }
+    for name, (shape, lengths, n_exp, kw, iters) in cases.items():
+        s = SHAPES[shape]
+        n_nom = int(np.sum(lengths))
+        eo, ea = synth_obs_acs(rng, n_exp, s["obs_dim"], s["acs_dim"], s["is_discrete"])
+        no, na = synth_obs_acs(rng, n_nom, s["obs_dim"], s["acs_dim"], s["is_discrete"])
+        no = no * 1.5 + 0.5
+        cn = make_cn(shape, seed=7, expert=(eo, ea), rng=rng, **kw)
+        mean = var = None
+        if kw.get("normalize"):
+            mean, var = cn.current_obs_mean, cn.current_obs_var
+        arrays = dict(expert_obs=eo, expert_acs=ea, nominal_obs=no, nominal_acs=na, lengths=np.array(lengths),
+                      iters=np.array(iters), lr=np.array(kw["lr"]), reg=np.array(kw.get("reg", 0.0)),
+                      per_step=np.array(kw.get("per_step", False)), no_is=np.array(kw.get("no_is", False)),
+                      tkon=np.array(kw.get("tkon", -1.0)), tkno=np.array(kw.get("tkno", -1.0)))
+        if mean is not None:
+            arrays.update(obs_mean=mean, obs_var=var)
+        arrays.update(sd_arrays("p0.", cn.network.state_dict()))
+        # two consecutive train() calls: Adam state persists across ICRL iterations (icrl/icrl.py:235)
+        for call in (1, 2):
+            m = cn.train(iters, no, na, np.array(lengths), mean, var, 1.0)
+            arrays.update(sd_arrays(f"p{call}.", cn.network.state_dict()))
+            arrays.update({f"m{call}.{k}": np.asarray(v, dtype=np.float64) for k, v in m.items()})
+            arrays.update({f"c{call}.{k}": v for k, v in opt_arrays(cn).items()})
+            if name == "hc_earlystop":
+                break
+        save(f"k2_{name}", **arrays)
+
+
+# ------------------------------------------------------------------------------------------- K3
+
+def golden_k3():
+    rng = np.random.default_rng(5)
+    for name, T, E, ep_len, lam_r, lam_c in (("small", 37, 3, 11, 0.95, 0.9), ("hc", 2048, 5, 1000, 0.95, 0.95),
+                                             ("ant", 2048, 5, 500, 0.9, 0.9), ("lam1", 64, 2, 1000, 1.0, 1.0),
+                                             ("wide", 256, 67, 50, 0.95, 0.97)):
+        buf = RolloutBufferWithCost(T, gym.spaces.Box(-1, 1, (3,)), gym.spaces.Box(-1, 1, (2,)), "cpu",
+                                    reward_gamma=0.99, reward_gae_lambda=lam_r, cost_gamma=0.98, cost_gae_lambda=lam_c,
+                                    n_envs=E)
+        for k in ("rewards", "reward_values", "costs", "cost_values"):
+            getattr(buf, k)[:] = rng.standard_normal((T, E)).astype(np.float32)
+        phase = rng.integers(0, ep_len, size=E)
+        t = np.arange(T)[:, None]
+        buf.dones[:] = (((t + phase[None]) % ep_len) == 0).astype(np.float32)
+        last_dones = rng.random(E) < 0.4
+        rlv = th.tensor(rng.standard_normal((E, 1)).astype(np.float32))
+        clv = th.tensor(rng.standard_normal((E, 1)).astype(np.float32))
+        ins = {k: getattr(buf, k).copy() for k in ("rewards", "reward_values", "costs", "cost_values", "dones")}
+        buf.compute_returns_and_advantage(rlv, clv, dones=last_dones)
+        save(f"k3_{name}", **ins, last_dones=last_dones, reward_last_value=rlv.numpy(), cost_last_value=clv.numpy(),
+             gammas=np.array([0.99, lam_r, 0.98, lam_c]),
+             reward_returns=buf.reward_returns, reward_advantages=buf.reward_advantages,
+             cost_returns=buf.cost_returns, cost_advantages=buf.cost_advantages)
+
+
+# ------------------------------------------------------------------------------------------- K4
+
+class FakeEnv(gym.Env):
+    def __init__(self, obs_dim, acs_dim, is_discrete):
+        self.observation_space = gym.spaces.Box(-np.inf, np.inf, (obs_dim,), np.float32)
+        self.action_space = gym.spaces.Discrete(acs_dim) if is_discrete else gym.spaces.Box(-1, 1, (acs_dim,), np.float32)
+
+    def reset(self):
+        return np.zeros(self.observation_space.shape, np.float32)
+
+    def step(self, a):
+        return self.reset(), 0.0, False, {}
+
+
+def golden_k4():
+    rng = np.random.default_rng(11)
+    cases = {
+        # name: shape, T, E, batch, epochs, kwargs
+        "hc": ("hc", 64, 4, 64, 3, dict(target_kl=0.01)),
+        "ant": ("ant", 128, 5, 128, 2, dict(learning_rate=3e-5, clip_range=0.4, penalty_initial_value=0.1,
+                                            penalty_learning_rate=0.05, target_kl=0.02)),
+        "lgw": ("lgw", 50, 4, 64, 2, dict(target_kl=0.01)),          # last minibatch is short (200 = 3*64 + 8)
+        "point": ("point", 48, 4, 64, 2, dict(target_kl=0.01, penalty_learning_rate=1.0, ent_coef=0.01)),
+        "hc_vfclip": ("hc", 32, 4, 32, 2, dict(clip_range_reward_vf=0.2, clip_range_cost_vf=0.3, ent_coef=0.02)),
+        "hc_fullbatch": ("hc", 32, 4, None, 1, dict()),              # exactly one optimiser step
+        "hc_klstop": ("hc", 64, 4, 64, 6, dict(target_kl=1e-6, learning_rate=3e-3)),
+    }
+    for name, (shape, T, E, bs, ne, kw) in cases.items():
+        s = SHAPES[shape]
+        env = DummyVecEnv([lambda s=s: FakeEnv(s["obs_dim"], s["acs_dim"], s["is_discrete"]) for _ in range(E)])
+        th.manual_seed(5)
+        algo = PPOLagrangian("TwoCriticsMlpPolicy", env, n_steps=T, batch_size=bs, n_epochs=ne, seed=3, device="cpu",
+                             **kw)
+        pol, buf = algo.policy, algo.rollout_buffer
+        obs, acs = synth_obs_acs(rng, T * E, s["obs_dim"], s["acs_dim"], s["is_discrete"], np.float32)
+        obs = np.clip(obs / 4.0, -10, 10).astype(np.float32)
+        buf.observations[:] = obs.reshape(T, E, -1)
+        buf.orig_observations[:] = obs.reshape(T, E, -1) * 2
+        buf.actions[:] = acs.reshape(T, E, -1)
+        for k in ("rewards", "costs", "orig_costs"):
+            getattr(buf, k)[:] = np.abs(rng.standard_normal((T, E))).astype(np.float32) * (0.2 if "cost" in k else 1.0)
+        buf.dones[:] = (rng.random((T, E)) < 0.02).astype(np.float32)
+        # values / log-probs from the policy itself on the stored (obs, action): ratio == 1 at the first step
+        with th.no_grad():
+            a = th.tensor(acs).long().flatten() if s["is_discrete"] else th.tensor(acs)
+            v, cv, lp, _ = pol.evaluate_actions(th.tensor(obs), a)
+        buf.reward_values[:] = v.numpy().reshape(T, E)
+        buf.cost_values[:] = cv.numpy().reshape(T, E)
+        buf.log_probs[:] = lp.numpy().reshape(T, E) + 0.05 * rng.standard_normal((T, E)).astype(np.float32)
+        buf.full, buf.pos = True, T
+        last_dones = rng.random(E) < 0.3
+        buf.compute_returns_and_advantage(v[-E:], cv[-E:], dones=last_dones)
+        arrays = {f"buf.{k}": getattr(buf, k).copy() for k in (
+            "observations", "actions", "log_probs", "reward_values", "reward_advantages",
+            "reward_returns", "cost_values", "cost_advantages", "cost_returns", "orig_costs")}
+        arrays.update(sd_arrays("p0.", pol.state_dict()))
+        arrays["param_order"] = np.array([n for n, _ in pol.named_parameters()])
+        arrays["nu0"] = algo.dual.nu().detach().numpy()
+        arrays["log_nu0"] = algo.dual.nu.log_nu.detach().numpy().copy()
+        logger.configure(folder=None, format_strings=[])
+        algo._current_progress_remaining = 1.0
+        np.random.seed(17)
+        algo.train()
+        arrays.update(sd_arrays("p1.", pol.state_dict()))
+        arrays.update({f"log.{k}": np.asarray(v, dtype=np.float64) for k, v in logger.Logger.CURRENT.name_to_value.items()})
+        arrays["log_nu1"] = algo.dual.nu.log_nu.detach().numpy().copy()
+        st = pol.optimizer.state_dict()["state"]
+        for i, k in enumerate(sorted(st)):
+            arrays[f"adam.{i}.exp_avg"] = st[k]["exp_avg"].numpy().copy()
+            arrays[f"adam.{i}.exp_avg_sq"] = st[k]["exp_avg_sq"].numpy().copy()
+            arrays[f"adam.{i}.step"] = np.asarray(float(st[k]["step"]))
+        hp = dict(batch_size=-1 if bs is None else bs, n_epochs=ne, numpy_seed=17, T=T, E=E,
+                  learning_rate=kw.get("learning_rate", 3e-4), clip_range=kw.get("clip_range", 0.2),
+                  target_kl=kw.get("target_kl", -1.0), ent_coef=kw.get("ent_coef", 0.0),
+                  penalty_initial_value=kw.get("penalty_initial_value", 1.0),
+                  penalty_learning_rate=kw.get("penalty_learning_rate", 0.01),
+                  clip_range_reward_vf=kw.get("clip_range_reward_vf", -1.0),
+                  clip_range_cost_vf=kw.get("clip_range_cost_vf", -1.0))
+        arrays.update({f"hp.{k}": np.asarray(v, dtype=np.float64) for k, v in hp.items()})
+        # a second train() on the same buffer: Adam moments / step counts / nu carry over
+        algo.train()
+        arrays.update(sd_arrays("p2.", pol.state_dict()))
+        arrays["log_nu2"] = algo.dual.nu.log_nu.detach().numpy().copy()
+        save(f"k4_{name}", **arrays)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["k1", "k2", "k3", "k4"]
+    for w in which:
+        globals()[f"golden_{w}"]()

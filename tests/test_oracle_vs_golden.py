@@ -1,0 +1,170 @@
+"""CPU: the oracle (oracle/*.py) against the fixtures produced by the unmodified reference (tests/golden)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch as th
+
+from conftest import GOLDEN, load_golden
+from helpers import COST_ATOL, COST_RTOL, SHAPES, cn_params, cn_spec, max_param_err, policy_params
+from oracle import cn as ocn
+from oracle import gae as ogae
+from oracle import ppo as oppo
+
+th.set_num_threads(1)
+
+
+@pytest.mark.parametrize("shape", list(SHAPES))
+@pytest.mark.parametrize("variant", ["raw", "norm"])
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+def test_k1_cost_matches_reference(shape, variant, tag):
+    d = load_golden(f"k1_{shape}_{variant}_{tag}")
+    spec = cn_spec(shape, d)
+    x = ocn.prepare_data(spec, d["obs"], d["acs"])
+    assert x.dtype == np.float32 and np.array_equal(x, d["x"])          # input prep is bit exact
+    cost = ocn.cost_function(cn_params(d), spec, d["obs"], d["acs"])
+    assert cost.dtype == np.float32 and cost.shape == d["cost"].shape
+    np.testing.assert_array_equal(cost, d["cost"])                       # same library, same arithmetic
+
+
+def test_k1_3d_input():
+    d = load_golden("k1_hc_3d")
+    cost = ocn.cost_function(cn_params(d), cn_spec("hc", d), d["obs"], d["acs"])
+    assert cost.shape == (6, 5)
+    np.testing.assert_array_equal(cost, d["cost"])
+
+
+def test_k1_real_checkpoints():
+    d = load_golden("k1_point_ckpt")
+    assert bool(d["loaded_clip_obs_is_none"]) and bool(d["loaded_action_high_is_none"])  # load() quirk a18
+    # after ConstraintNet.load: no obs clipping, no action clipping, raw inputs, select [0,1]
+    spec = ocn.CNSpec(6, 2, tuple(d["hidden_sizes"]), False, obs_select_dim=[0, 1], acs_select_dim=[-1], clip_obs=None)
+    assert spec.select_dim == list(d["select_dim"])
+    np.testing.assert_array_equal(ocn.cost_function(cn_params(d), spec, d["obs"], d["acs"]), d["cost"])
+    d = load_golden("k1_antbroken_ckpt")
+    spec = ocn.CNSpec(113, 8, tuple(d["hidden_sizes"]), False, clip_obs=None)
+    np.testing.assert_array_equal(ocn.cost_function(cn_params(d), spec, d["obs"], d["acs"]), d["cost"])
+    d = load_golden("k1_ant_expert_slice")
+    np.testing.assert_array_equal(ocn.cost_function(cn_params(d), cn_spec("ant", d), d["obs"], d["acs"]), d["cost"])
+
+
+K2_CASES = sorted(os.path.basename(p)[3:-4] for p in glob.glob(os.path.join(GOLDEN, "k2_*.npz")))
+
+
+@pytest.mark.parametrize("case", K2_CASES)
+def test_k2_train_matches_reference(case):
+    d = load_golden(f"k2_{case}")
+    shape = case.split("_")[0]
+    spec = cn_spec(shape, d, regularizer_coeff=float(d["reg"]), importance_sampling=not bool(d["no_is"]),
+                   per_step_importance_sampling=bool(d["per_step"]), target_kl_old_new=float(d["tkon"]),
+                   target_kl_new_old=float(d["tkno"]))
+    params = cn_params(d, "p0.")
+    adam = ocn.adam_init(params)
+    for call in (1, 2):
+        if f"p{call}.0.weight" not in d:
+            break
+        m = ocn.train(params, adam, spec, int(d["iters"]), d["nominal_obs"], d["nominal_acs"], d["lengths"],
+                      d["expert_obs"], d["expert_acs"], lr=float(d["lr"]), materialize_broadcast=True)
+        ref = cn_params(d, f"p{call}.")
+        assert max_param_err([p.numpy() for p in params], [p.numpy() for p in ref]) <= 1e-6
+        for k, v in m.items():
+            r = float(d[f"m{call}.{k}"])
+            if np.isnan(r) or np.isinf(r):
+                assert (np.isnan(v) and np.isnan(r)) or v == r, k
+            else:
+                assert abs(v - r) <= 1e-5 * max(abs(r), 1e-2), (k, v, r)
+        nstep = float(d[f"c{call}.adam.0.step"])
+        assert adam["step"] == nstep
+
+
+@pytest.mark.parametrize("case", ["hc_perstep_mild", "ant_perstep"])
+def test_k2_quirk_a_identity(case):
+    """mean over the reference's [N,N,1] broadcast == mean(w) * mean(log p): the O(N) form the product uses."""
+    d = load_golden(f"k2_{case}")
+    spec = cn_spec(case.split("_")[0], d, regularizer_coeff=float(d["reg"]), per_step_importance_sampling=True,
+                   target_kl_old_new=float(d["tkon"]), target_kl_new_old=float(d["tkno"]))
+    params = cn_params(d, "p0.")
+    ocn.train(params, ocn.adam_init(params), spec, int(d["iters"]), d["nominal_obs"], d["nominal_acs"], d["lengths"],
+              d["expert_obs"], d["expert_acs"], lr=float(d["lr"]), materialize_broadcast=False)
+    ref = cn_params(d, "p1.")
+    assert max_param_err([p.numpy() for p in params], [p.numpy() for p in ref]) <= 1e-4
+
+
+K3_CASES = sorted(os.path.basename(p)[3:-4] for p in glob.glob(os.path.join(GOLDEN, "k3_*.npz")))
+
+
+@pytest.mark.parametrize("case", K3_CASES)
+def test_k3_gae_bit_exact(case):
+    d = load_golden(f"k3_{case}")
+    g = d["gammas"]
+    out = ogae.dual_gae(d["rewards"], d["reward_values"], d["costs"], d["cost_values"], d["dones"],
+                        d["reward_last_value"], d["cost_last_value"], d["last_dones"], g[0], g[1], g[2], g[3])
+    for k, v in out.items():
+        assert v.dtype == np.float32
+        np.testing.assert_array_equal(v, d[k])
+
+
+K4_CASES = sorted(os.path.basename(p)[3:-4] for p in glob.glob(os.path.join(GOLDEN, "k4_*.npz")))
+
+
+def k4_inputs(d):
+    flat = {
+        "observations": ogae.env_major(d["buf.observations"]), "actions": ogae.env_major(d["buf.actions"]),
+        "old_log_prob": ogae.env_major(d["buf.log_probs"]), "old_reward_values": ogae.env_major(d["buf.reward_values"]),
+        "reward_advantages": ogae.env_major(d["buf.reward_advantages"]),
+        "reward_returns": ogae.env_major(d["buf.reward_returns"]),
+        "old_cost_values": ogae.env_major(d["buf.cost_values"]),
+        "cost_advantages": ogae.env_major(d["buf.cost_advantages"]),
+        "cost_returns": ogae.env_major(d["buf.cost_returns"]),
+    }
+    hp = {k[3:]: float(v) for k, v in d.items() if k.startswith("hp.")}
+    return flat, hp
+
+
+def k4_kwargs(hp, is_discrete, nu):
+    opt = lambda k: None if hp[k] < 0 else hp[k]
+    return dict(is_discrete=is_discrete, batch_size=None if hp["batch_size"] < 0 else int(hp["batch_size"]),
+                n_epochs=int(hp["n_epochs"]), lr=hp["learning_rate"], clip_range=hp["clip_range"], nu=nu,
+                ent_coef=hp["ent_coef"], target_kl=opt("target_kl"), clip_range_reward_vf=opt("clip_range_reward_vf"),
+                clip_range_cost_vf=opt("clip_range_cost_vf"))
+
+
+@pytest.mark.parametrize("case", K4_CASES)
+def test_k4_train_matches_reference(case):
+    d = load_golden(f"k4_{case}")
+    is_discrete = "log_std" not in [str(n) for n in d["param_order"]]
+    flat, hp = k4_inputs(d)
+    P = policy_params(d, "p0.")
+    adam = ocn.adam_init(list(P.values()))
+    dual = oppo.dual_init(hp["penalty_initial_value"])
+    assert np.allclose(dual["log_nu"].numpy(), d["log_nu0"], rtol=0, atol=0)
+    n = flat["observations"].shape[0]
+    for call in (1, 2):
+        if call == 1:
+            np.random.seed(int(hp["numpy_seed"]))
+        nu = oppo.dual_nu(dual).item()
+        # the reference draws one permutation per epoch it actually runs (buffers.py:596)
+        perms = []
+
+        class LazyPerms:
+            def __getitem__(self, e):
+                while len(perms) <= e:
+                    perms.append(np.random.permutation(n))
+                return perms[e]
+        out = oppo.train(P, adam, flat, LazyPerms(), **k4_kwargs(hp, is_discrete, nu))
+        oppo.dual_step(dual, np.mean(d["buf.orig_costs"]), 0.0, hp["penalty_learning_rate"])
+        ref = policy_params(d, f"p{call}.")
+        err = max_param_err([p.numpy() for p in P.values()], [p.numpy() for p in ref.values()])
+        assert err <= 2e-5, err
+        assert np.allclose(dual["log_nu"].numpy(), d[f"log_nu{call}"], rtol=1e-6)
+        if call == 1:
+            log = {k[4:]: float(v) for k, v in d.items() if k.startswith("log.")}
+            ps = out["per_step"]
+            chk = {"train/entropy_loss": np.mean(ps["entropy_loss"]), "train/policy_gradient_loss": np.mean(ps["pg_loss"]),
+                   "train/reward_value_loss": np.mean(ps["reward_value_loss"]),
+                   "train/cost_value_loss": np.mean(ps["cost_value_loss"]),
+                   "train/clip_fraction": np.mean(ps["clip_fraction"]), "train/loss": ps["loss"][-1],
+                   "train/approx_kl": out["last_epoch_approx_kl"], "train/early_stop_epoch": out["early_stop_epoch"]}
+            for k, v in chk.items():
+                assert abs(v - log[k]) <= 1e-5 * max(abs(log[k]), 1e-2), (k, v, log[k])
