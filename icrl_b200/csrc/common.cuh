@@ -1,0 +1,117 @@
+// Shared device/host helpers for the icrl_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/icrl_b200.h"
+
+namespace icrl {
+
+// ---------------------------------------------------------------- host-side error plumbing
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define ICRL_CHECK_ARG(cond, ...)                 \
+    do {                                          \
+        if (!(cond)) {                            \
+            ::icrl::set_error(__VA_ARGS__);       \
+            return ICRL_EINVAL;                   \
+        }                                         \
+    } while (0)
+
+#define ICRL_CUDA(call)                                                                         \
+    do {                                                                                        \
+        cudaError_t err__ = (call);                                                             \
+        if (err__ != cudaSuccess) {                                                             \
+            ::icrl::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+            return (int)err__;                                                                  \
+        }                                                                                       \
+    } while (0)
+
+#define ICRL_LAUNCH_CHECK()                                                                     \
+    do {                                                                                        \
+        cudaError_t err__ = cudaGetLastError();                                                 \
+        if (err__ != cudaSuccess) {                                                             \
+            ::icrl::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(err__), __FILE__, __LINE__); \
+            return (int)err__;                                                                  \
+        }                                                                                       \
+        ::icrl::count_launch();                                                                 \
+    } while (0)
+
+int sm_count();
+
+// grow-only device / pinned-host scratch, one slot per purpose (not thread safe: the learner is single threaded,
+// as the reference's is -- SURVEY §8b "Threading").
+enum Slot { SLOT_IN0 = 0, SLOT_IN1, SLOT_OUT0, SLOT_WORK0, SLOT_WORK1, SLOT_WORK2, SLOT_WORK3, SLOT_COUNT };
+int device_scratch(Slot s, size_t bytes, void** ptr);
+int pinned_scratch(Slot s, size_t bytes, void** ptr);
+
+// ---------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+
+constexpr int kWarp = 32;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier + 1-D bulk async copy (TMA, `cp.async.bulk` -> SASS UBLKCP): global -> shared::cta
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// bytes must be a multiple of 16; src and dst 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// streaming (read-once) global loads that do not pollute L1
+__device__ __forceinline__ float ld_stream(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace icrl
