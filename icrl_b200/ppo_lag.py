@@ -1,0 +1,386 @@
+"""PPOLagrangian -- host-side mirror of stable_baselines3/ppo_lag/ppo_lag.py:17-365 and of the
+OnPolicyWithCostAlgorithm plumbing it inherits (common/on_policy_algorithm.py:258-497, base_class.py).
+
+`train()` is the learner hot path: the rollout buffer's fields are staged to HBM once, numpy's per-epoch
+permutations are drawn on the host (global numpy RNG, as buffers.py:596 does) and ONE persistent cluster kernel
+(K4, csrc/k4_ppo_lag.cu) runs every minibatch of every epoch, the global-norm clip, Adam and the target_kl early
+stop.  The dual step (dual_variable.py:47-57) follows as a second tiny launch.  `learn()` / `collect_rollouts()`
+keep the reference's control flow; env stepping stays on the host (north_star (c)).
+"""
+import ctypes as C
+import time
+from typing import Any, Callable, Dict, Optional, Union
+
+import numpy as np
+import torch as th
+
+from . import _lib, logger
+from .buffers import RolloutBufferWithCost
+from .device import resolve_device
+from .dual_variable import DualVariable, PIDLagrangian
+from .policies import ActorTwoCriticsPolicy
+from .spaces import is_discrete as _is_discrete
+
+POLICIES = {"TwoCriticsMlpPolicy": ActorTwoCriticsPolicy}
+
+
+def get_schedule_fn(value_schedule):
+    """stable_baselines3/common/utils.py:74-91: constants become constant schedules of progress_remaining."""
+    if isinstance(value_schedule, (float, int)):
+        v = float(value_schedule)
+        return lambda _: v
+    assert callable(value_schedule)
+    return value_schedule
+
+
+def explained_variance(y_pred: np.ndarray, y_true: np.ndarray) -> np.ndarray:
+    """stable_baselines3/common/utils.py:43-59."""
+    assert y_true.ndim == 1 and y_pred.ndim == 1
+    var_y = np.var(y_true)
+    return np.nan if var_y == 0 else 1 - np.var(y_true - y_pred) / var_y
+
+
+class _NullCallback:
+    def init_callback(self, model): pass
+    def on_training_start(self, locals_, globals_): pass
+    def on_rollout_start(self): pass
+    def update_locals(self, locals_): pass
+    def on_step(self): return True
+    def on_rollout_end(self): pass
+    def on_training_end(self): pass
+
+
+class _CallbackList(_NullCallback):
+    def __init__(self, callbacks): self.callbacks = list(callbacks)
+    def init_callback(self, model): [c.init_callback(model) for c in self.callbacks]
+    def on_training_start(self, l, g): [c.on_training_start(l, g) for c in self.callbacks]
+    def on_rollout_start(self): [c.on_rollout_start() for c in self.callbacks]
+    def update_locals(self, l): [c.update_locals(l) for c in self.callbacks if hasattr(c, "update_locals")]
+    def on_step(self): return all(c.on_step() is not False for c in self.callbacks)
+    def on_rollout_end(self): [c.on_rollout_end() for c in self.callbacks]
+    def on_training_end(self): [c.on_training_end() for c in self.callbacks]
+
+
+class PPOLagrangian:
+    def __init__(
+        self,
+        policy: Union[str, type],
+        env,
+        algo_type: str = 'lagrangian',
+        learning_rate: Union[float, Callable] = 3e-4,
+        n_steps: int = 2048,
+        batch_size: Optional[int] = 64,
+        n_epochs: int = 10,
+        reward_gamma: float = 0.99,
+        reward_gae_lambda: float = 0.95,
+        cost_gamma: float = 0.99,
+        cost_gae_lambda: float = 0.95,
+        clip_range: float = 0.2,
+        clip_range_reward_vf: Optional[float] = None,
+        clip_range_cost_vf: Optional[float] = None,
+        ent_coef: float = 0.0,
+        reward_vf_coef: float = 0.5,
+        cost_vf_coef: float = 0.5,
+        max_grad_norm: float = 0.5,
+        use_sde: bool = False,
+        sde_sample_freq: int = -1,
+        target_kl: Optional[float] = None,
+        penalty_initial_value: float = 1,
+        penalty_learning_rate: float = 0.01,
+        penalty_min_value: Optional[float] = None,
+        update_penalty_after: int = 1,
+        budget: float = 0.,
+        tensorboard_log: Optional[str] = None,
+        create_eval_env: bool = False,
+        pid_kwargs: Optional[Dict[str, Any]] = None,
+        policy_kwargs: Optional[Dict[str, Any]] = None,
+        verbose: int = 0,
+        seed: Optional[int] = None,
+        device: Union[th.device, str] = "auto",
+        _init_setup_model: bool = True,
+    ):
+        if use_sde:
+            raise NotImplementedError("gSDE is not used by the ICRL configs and not implemented")
+        self.policy_class = POLICIES[policy] if isinstance(policy, str) else policy
+        self.env = env
+        self.observation_space, self.action_space = env.observation_space, env.action_space
+        self.n_envs = getattr(env, "num_envs", 1)
+        self.algo_type, self.learning_rate = algo_type, learning_rate
+        self.n_steps, self.batch_size, self.n_epochs = n_steps, batch_size, n_epochs
+        self.reward_gamma, self.reward_gae_lambda = reward_gamma, reward_gae_lambda
+        self.cost_gamma, self.cost_gae_lambda = cost_gamma, cost_gae_lambda
+        self.clip_range, self.clip_range_reward_vf, self.clip_range_cost_vf = clip_range, clip_range_reward_vf, clip_range_cost_vf
+        self.ent_coef, self.reward_vf_coef, self.cost_vf_coef = ent_coef, reward_vf_coef, cost_vf_coef
+        self.max_grad_norm, self.target_kl = max_grad_norm, target_kl
+        self.use_sde, self.sde_sample_freq = use_sde, sde_sample_freq
+        self.penalty_initial_value, self.penalty_learning_rate = penalty_initial_value, penalty_learning_rate
+        self.penalty_min_value, self.update_penalty_after = penalty_min_value, update_penalty_after
+        self.budget, self.pid_kwargs = budget, pid_kwargs
+        self.policy_kwargs = {} if policy_kwargs is None else policy_kwargs
+        self.verbose, self.seed = verbose, seed
+        self.device = resolve_device(device)
+        self.num_timesteps, self._total_timesteps, self._n_updates = 0, 0, 0
+        self._current_progress_remaining = 1
+        self._last_obs = self._last_original_obs = self._last_dones = None
+        self.start_time = None
+        self.rollout_buffer = None
+        self.ep_info_buffer = None
+        self._staging = {}
+        if _init_setup_model:
+            self._setup_model()
+
+    # ---------------------------------------------------------------- setup (on_policy_algorithm.py:316-338, ppo_lag.py:145-175)
+    def set_random_seed(self, seed: Optional[int] = None) -> None:
+        """stable_baselines3/common/utils.py:23-40 + base_class.py:540-558."""
+        if seed is None:
+            return
+        import random
+        random.seed(seed)
+        np.random.seed(seed)
+        th.manual_seed(seed)
+        if hasattr(self.action_space, "seed"):
+            self.action_space.seed(seed)
+        if self.env is not None and hasattr(self.env, "seed"):
+            self.env.seed(seed)
+
+    def _setup_model(self) -> None:
+        self.lr_schedule = get_schedule_fn(self.learning_rate)
+        self.set_random_seed(self.seed)
+        self.rollout_buffer = RolloutBufferWithCost(
+            self.n_steps, self.observation_space, self.action_space, self.device, reward_gamma=self.reward_gamma,
+            reward_gae_lambda=self.reward_gae_lambda, cost_gamma=self.cost_gamma, cost_gae_lambda=self.cost_gae_lambda,
+            n_envs=self.n_envs)
+        self.policy = self.policy_class(self.observation_space, self.action_space, self.lr_schedule, use_sde=self.use_sde,
+                                        device=self.device, **self.policy_kwargs)
+        if self.algo_type == 'lagrangian':
+            self.dual = DualVariable(self.budget, self.penalty_learning_rate, self.penalty_initial_value,
+                                     self.penalty_min_value, device=self.device)
+        elif self.algo_type == 'pidlagrangian':
+            kw = self.pid_kwargs
+            self.dual = PIDLagrangian(alpha=kw['alpha'], penalty_init=kw['penalty_init'], Kp=kw['Kp'], Ki=kw['Ki'],
+                                      Kd=kw['Kd'], pid_delay=kw['pid_delay'], delta_p_ema_alpha=kw['delta_p_ema_alpha'],
+                                      delta_d_ema_alpha=kw['delta_d_ema_alpha'])
+        else:
+            raise ValueError("Unrecognized value for argument 'algo_type' in PPOLagrangian")
+        self.clip_range = get_schedule_fn(self.clip_range)
+        for name in ("clip_range_reward_vf", "clip_range_cost_vf"):
+            v = getattr(self, name)
+            if v is not None:
+                if isinstance(v, (float, int)):
+                    assert v > 0, "`clip_range_vf` must be positive, pass `None` to deactivate vf clipping"
+                setattr(self, name, get_schedule_fn(v))
+
+    def _update_learning_rate(self, optimizer) -> None:
+        """base_class.py:213-227."""
+        lr = self.lr_schedule(self._current_progress_remaining)
+        logger.record("train/learning_rate", lr)
+        for g in optimizer.param_groups:
+            g["lr"] = lr
+
+    def _update_current_progress_remaining(self, num_timesteps: int, total_timesteps: int) -> None:
+        self._current_progress_remaining = 1.0 - float(num_timesteps) / float(total_timesteps)
+
+    # ---------------------------------------------------------------- K4
+    def _stage(self, name: str, host: np.ndarray) -> th.Tensor:
+        """host array -> persistent pinned staging buffer -> persistent device buffer (async on the current stream)."""
+        slot = self._staging.get(name)
+        if slot is None or slot[0].shape != host.shape or slot[0].dtype != th.from_numpy(host[:0]).dtype:
+            pinned = th.empty(host.shape, dtype=th.from_numpy(host[:0]).dtype).pin_memory()
+            slot = (pinned, th.empty(host.shape, dtype=pinned.dtype, device=self.device))
+            self._staging[name] = slot
+        slot[0].numpy()[...] = host
+        slot[1].copy_(slot[0], non_blocking=True)
+        return slot[1]
+
+    def train(self) -> None:
+        """ppo_lag.py:177-338."""
+        self._update_learning_rate(self.policy.optimizer)
+        clip_range = self.clip_range(self._current_progress_remaining)
+        clip_range_reward_vf = clip_range_cost_vf = None
+        if self.clip_range_reward_vf is not None:
+            clip_range_reward_vf = self.clip_range_reward_vf(self._current_progress_remaining)
+        if self.clip_range_cost_vf is not None:
+            clip_range_cost_vf = self.clip_range_cost_vf(self._current_progress_remaining)
+
+        buf = self.rollout_buffer
+        assert buf.full, ""
+        T, E = buf.buffer_size, buf.n_envs
+        n = T * E
+        # numpy draws one permutation per epoch that actually runs (buffers.py:596); draw them all, remember the RNG
+        # state after each, and rewind to the right one once the device reports where it stopped.
+        perms = np.empty((self.n_epochs, n), dtype=np.int32)
+        rng_states = []
+        for e in range(self.n_epochs):
+            perms[e] = np.random.permutation(n)
+            rng_states.append(np.random.get_state())
+        buf._flatten_once()          # the reference's public arrays become env-major on the first get()
+
+        rename = {"log_probs": "old_log_prob", "reward_values": "old_reward_values", "cost_values": "old_cost_values"}
+        data = _lib.PpoData()
+        keep = []
+        for name in ("observations", "actions", "log_probs", "reward_values", "reward_advantages", "reward_returns",
+                     "cost_values", "cost_advantages", "cost_returns"):
+            dev = self._stage(name, np.ascontiguousarray(buf.time_major(name), dtype=np.float32))
+            keep.append(dev)
+            setattr(data, rename.get(name, name), dev.data_ptr())
+        perm_dev = self._stage("perm", perms)
+        data.perm = perm_dev.data_ptr()
+
+        current_penalty = self.dual.nu().item()
+        pol = self.policy
+        steps_per_epoch = (n + (self.batch_size or n) - 1) // (self.batch_size or n)
+        cfg = pol.make_cfg(
+            T=T, E=E, batch_size=int(self.batch_size or 0), n_epochs=self.n_epochs,
+            has_target_kl=int(self.target_kl is not None), target_kl=float(self.target_kl or 0.0),
+            has_clip_vf_reward=int(clip_range_reward_vf is not None), clip_range_reward_vf=float(clip_range_reward_vf or 0.0),
+            has_clip_vf_cost=int(clip_range_cost_vf is not None), clip_range_cost_vf=float(clip_range_cost_vf or 0.0),
+            clip_range=float(clip_range), ent_coef=float(self.ent_coef), reward_vf_coef=float(self.reward_vf_coef),
+            cost_vf_coef=float(self.cost_vf_coef), max_grad_norm=float(self.max_grad_norm), nu=float(current_penalty),
+            max_steps=int(getattr(self, "_max_steps", 0)))
+        stats = th.zeros(self.n_epochs * steps_per_epoch, _lib.PPO_STATS_PER_STEP, device=self.device)
+        result = th.zeros(4, dtype=th.int32, device=self.device)
+        with th.cuda.device(self.device):
+            _lib.check(_lib.lib().icrl_ppo_train(
+                C.byref(cfg), C.byref(data), _lib.ptr(pol._params), _lib.ptr(pol._adam_m), _lib.ptr(pol._adam_v),
+                pol.optimizer.step_count, _lib.ptr(stats), _lib.ptr(result), _lib.current_stream()))
+        result_h = result.cpu()                                   # synchronises
+        early_stop_epoch, steps = int(result_h[0]), int(result_h[1])
+        pol.optimizer.step_count += steps
+        epochs_run = min(self.n_epochs, early_stop_epoch + 1)
+        np.random.set_state(rng_states[epochs_run - 1])
+        st = stats[:steps].cpu().numpy()
+        self.last_train_stats = st
+        pg_losses, clip_fractions = st[:, 0], st[:, 1]
+        reward_value_losses, cost_value_losses, entropy_losses = st[:, 2], st[:, 3], st[:, 4]
+        last_epoch_kl = st[(epochs_run - 1) * steps_per_epoch:, 5]
+        f32 = np.float32
+        last_loss = (f32(st[-1, 0]) + f32(self.ent_coef) * f32(st[-1, 4]) + f32(self.reward_vf_coef) * f32(st[-1, 2])
+                     + f32(self.cost_vf_coef) * f32(st[-1, 3]))
+
+        self._n_updates += self.n_epochs
+        # dual update with the original (un-normalised) cost, ppo_lag.py:301-306
+        average_cost = np.mean(buf.orig_costs)
+        total_cost = np.sum(buf.orig_costs)
+        if self.update_penalty_after is None or ((self._n_updates / self.n_epochs) % self.update_penalty_after == 0):
+            self.dual.update_parameter(average_cost)
+
+        logger.record("train/entropy_loss", np.mean(entropy_losses.astype(np.float64)))
+        logger.record("train/policy_gradient_loss", np.mean(pg_losses.astype(np.float64)))
+        logger.record("train/reward_value_loss", np.mean(reward_value_losses.astype(np.float64)))
+        logger.record("train/cost_value_loss", np.mean(cost_value_losses.astype(np.float64)))
+        logger.record("train/approx_kl", np.mean(last_epoch_kl))
+        logger.record("train/clip_fraction", np.mean(clip_fractions.astype(np.float64)))
+        logger.record("train/loss", float(last_loss))
+        logger.record("train/mean_reward_advantages", np.mean(buf.reward_advantages.flatten()))
+        logger.record("train/mean_cost_advantages", np.mean(buf.cost_advantages.flatten()))
+        logger.record("train/reward_explained_variance",
+                      explained_variance(buf.reward_returns.flatten(), buf.reward_values.flatten()))
+        logger.record("train/cost_explained_variance",
+                      explained_variance(buf.cost_returns.flatten(), buf.cost_values.flatten()))
+        logger.record("train/nu", self.dual.nu().item())
+        logger.record("train/nu_loss", self.dual.loss.item())
+        logger.record("train/average_cost", average_cost)
+        logger.record("train/total_cost", total_cost)
+        logger.record("train/early_stop_epoch", early_stop_epoch)
+        if not pol.is_discrete:
+            logger.record("train/std", th.exp(pol.log_std).mean().item())
+        logger.record("train/n_updates", self._n_updates, exclude="tensorboard")
+        logger.record("train/clip_range", clip_range)
+        if clip_range_reward_vf is not None:
+            logger.record("train/clip_range_reward_vf", clip_range_reward_vf)
+        if clip_range_cost_vf is not None:
+            logger.record("train/clip_range_cost_vf", clip_range_cost_vf)
+
+    # ---------------------------------------------------------------- rollouts (on_policy_algorithm.py:340-421)
+    def _init_callback(self, callback):
+        if callback is None:
+            callback = _NullCallback()
+        elif isinstance(callback, (list, tuple)):
+            callback = _CallbackList(callback)
+        if hasattr(callback, "init_callback"):
+            callback.init_callback(self)
+        return callback
+
+    def _setup_learn(self, total_timesteps, callback, reset_num_timesteps=True):
+        """base_class.py:479-538 (without eval-env / Monitor plumbing)."""
+        self.start_time = time.time()
+        if reset_num_timesteps:
+            self.num_timesteps = 0
+        else:
+            total_timesteps += self.num_timesteps
+        self._total_timesteps = total_timesteps
+        if reset_num_timesteps or self._last_obs is None:
+            self._last_obs = self.env.reset()
+            self._last_dones = np.zeros((self.n_envs,), dtype=bool)
+            self._last_original_obs = (self.env.get_original_obs() if hasattr(self.env, "get_original_obs")
+                                       else self._last_obs)
+        return total_timesteps, self._init_callback(callback)
+
+    def collect_rollouts(self, env, callback, rollout_buffer, n_rollout_steps: int, cost_function) -> bool:
+        assert self._last_obs is not None, "No previous observation was provided"
+        n_steps = 0
+        rollout_buffer.reset()
+        callback.on_rollout_start()
+        has_orig_obs = hasattr(env, "get_original_obs")
+        discrete = _is_discrete(self.action_space)
+        while n_steps < n_rollout_steps:
+            actions, reward_values, cost_values, log_probs = self.policy.forward(th.as_tensor(np.asarray(self._last_obs)))
+            actions = actions.numpy()
+            clipped_actions = actions
+            if not discrete:
+                clipped_actions = np.clip(actions, self.action_space.low, self.action_space.high)
+            new_obs, rewards, dones, infos = env.step(clipped_actions)
+            orig_obs = env.get_original_obs() if has_orig_obs else new_obs
+            if type(cost_function) is str:
+                costs = np.array([info.get(cost_function, 0) for info in infos])
+                orig_costs = env.get_original_cost() if hasattr(env, "get_original_cost") else costs
+            else:
+                costs = cost_function(orig_obs.copy(), clipped_actions)
+                orig_costs = costs
+            self.num_timesteps += env.num_envs
+            callback.update_locals(locals())
+            if callback.on_step() is False:
+                return False
+            n_steps += 1
+            if discrete:
+                actions = actions.reshape(-1, 1)
+            rollout_buffer.add(self._last_obs, self._last_original_obs, new_obs, orig_obs, actions, rewards, costs,
+                               orig_costs, self._last_dones, reward_values, cost_values, log_probs)
+            self._last_obs, self._last_original_obs, self._last_dones = new_obs, orig_obs, dones
+        rollout_buffer.compute_returns_and_advantage(reward_values, cost_values, dones=dones)
+        callback.on_rollout_end()
+        return True
+
+    def learn(self, total_timesteps: int, cost_function: Union[str, Callable], callback=None, log_interval: int = 1,
+              eval_env=None, eval_freq: int = -1, n_eval_episodes: int = 5, tb_log_name: str = "PPOLagrangian",
+              eval_log_path: Optional[str] = None, reset_num_timesteps: bool = True) -> "PPOLagrangian":
+        """on_policy_algorithm.py:430-492."""
+        iteration = 0
+        total_timesteps, callback = self._setup_learn(total_timesteps, callback, reset_num_timesteps)
+        callback.on_training_start(locals(), globals())
+        while self.num_timesteps < total_timesteps:
+            if self.collect_rollouts(self.env, callback, self.rollout_buffer, self.n_steps, cost_function) is False:
+                break
+            iteration += 1
+            self._update_current_progress_remaining(self.num_timesteps, total_timesteps)
+            if log_interval is not None and iteration % log_interval == 0:
+                fps = int(self.num_timesteps / max(time.time() - self.start_time, 1e-9))
+                logger.record("time/iterations", iteration, exclude="tensorboard")
+                logger.record("time/fps", fps)
+                logger.record("time/total_timesteps", self.num_timesteps, exclude="tensorboard")
+                logger.dump(step=self.num_timesteps)
+            self.train()
+        callback.on_training_end()
+        return self
+
+    def predict(self, observation, state=None, mask=None, deterministic: bool = False):
+        return self.policy.predict(observation, state, mask, deterministic)
+
+    # ---------------------------------------------------------------- checkpoints (tensors only)
+    def get_parameters(self):
+        return {"policy": self.policy.state_dict(), "policy.optimizer": self.policy.optimizer.state_dict()}
+
+    def set_parameters(self, params):
+        self.policy.load_state_dict(params["policy"])
+        if "policy.optimizer" in params:
+            self.policy.optimizer.load_state_dict(params["policy.optimizer"])

@@ -197,10 +197,11 @@ int icrl_ppo_train(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* pa
 int icrl_policy_forward(const icrl_ppo_cfg* cfg, const float* params, const float* obs, int64_t n,
                         float* head, float* values, float* cost_values, void* stream);
 
-/* Dual variable -- replaces DualVariable.update_parameter (stable_baselines3/common/dual_variable.py:47-57):
- * state is device float32[4] = {log_nu, adam_m, adam_v, last_loss}; step counts from 1.  mean_cost is read from
- * the device (`mean_of` [n] float32 is averaged in float32 pairwise as np.mean does when mean_of != NULL,
- * else *mean_cost_dev is used).  Also writes nu = softplus(log_nu) after the step to state[3]... see .cu */
+/* Dual variable -- replaces DualVariable.update_parameter + Nu.clamp (stable_baselines3/common/dual_variable.py:
+ * 27-29,47-57) and the np.mean(rollout_buffer.orig_costs) feeding it (ppo_lag.py:303-306).  `state` is device
+ * float32[6] = {log_nu, adam exp_avg, adam exp_avg_sq, last loss, nu = softplus(log_nu) after the step, mean cost};
+ * the first three are read and updated, the rest written.  orig_costs is device float32 [n].  Adam uses the
+ * reference's defaults for this optimiser (betas 0.9/0.999, eps 1e-8); adam_step_before counts previous updates. */
 int icrl_dual_update(float* state, const float* orig_costs, int64_t n, double alpha, double lr, int64_t adam_step_before,
                      double clamp_min_log_nu, void* stream);
 
