@@ -283,10 +283,12 @@ class ConstraintNet:
         for g in self.optimizer.param_groups:                # stable_baselines3/common/utils.py:62-71
             g["lr"] = self.lr_schedule(current_progress_remaining)
 
-    def _expert_on_device(self):
-        if self._expert_dev is None:
+    def _expert_on_device(self, obs_dtype):
+        """The expert batch is uploaded once and stays resident in HBM across ICRL iterations."""
+        if self._expert_dev is None or self._expert_dev[0].dtype != obs_dtype:
             eo, ea, _ = self._host_inputs(self.expert_obs, self.expert_acs)
-            self._expert_dev = (th.from_numpy(eo).to(self._dev), th.from_numpy(ea).to(self._dev))
+            eo_dev = th.from_numpy(eo).to(self._dev).to(obs_dtype)
+            self._expert_dev = (eo_dev, th.from_numpy(ea).to(self._dev))
         return self._expert_dev
 
     def train(
@@ -310,7 +312,11 @@ class ConstraintNet:
         assert int(lengths.sum()) <= no.shape[0]
         offsets = np.zeros(len(lengths) + 1, dtype=np.int32)
         offsets[1:] = np.cumsum(lengths)
-        eo_dev, ea_dev = self._expert_on_device()
+        exp_is_f64 = np.asarray(self.expert_obs).dtype != np.float32
+        if exp_is_f64 and no.dtype != np.float64:
+            no = no.astype(np.float64)
+        eo_dev, ea_dev = self._expert_on_device(th.float64 if no.dtype == np.float64 else th.float32)
+        assert int(lengths.sum()) == no.shape[0] or not self.importance_sampling, "episode_lengths must cover nominal_obs"
         no_dev, na_dev = th.from_numpy(no).to(self._dev), th.from_numpy(na).to(self._dev)
         off_dev = th.from_numpy(offsets).to(self._dev)
         g = self.optimizer.param_groups[0]
