@@ -1,0 +1,442 @@
+#!/usr/bin/env python
+"""bench.py -- learner transitions/sec per ICRL iteration (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload halfcheetah|antwall|lapgrid|pointcircle]
+    python bench.py --impl reference ...      # the reference's CPU algorithm (oracle port) on the host cores
+
+One "step" = one full ICRL learner iteration on synthetic buffers of the named env's shape:
+    R rollouts x (K1 cost relabel + K3 dual GAE + K4 PPO-Lagrangian update + dual step)  +  one K2 constraint-net train.
+`value`  : whole-job transitions/s with all inputs resident in HBM (icrl_b200.learner.DeviceLearner, C-ABI device entry points).
+`e2e`    : the same iteration through the reference-shaped Python API with HOST (numpy) buffers: ConstraintNet.cost_function,
+           RolloutBufferWithCost.compute_returns_and_advantage, PPOLagrangian.train, ConstraintNet.train -- H2D / D2H inside.
+`roofline`: the dominant kernel (K4 persistent PPO kernel), algorithmic bytes / measured launch duration vs measured HBM peak.
+`cpu_baseline`: the oracle (CPU restatement of the reference, torch-CPU + numpy) on a bounded sample, extrapolated linearly.
+Fixed work: KL early stops (ppo target_kl, cn target_kl_*) are disabled so every epoch / backward iteration runs.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch as th  # noqa: E402
+
+METRIC = "learner transitions/sec per ICRL iteration"
+UNIT = "transitions/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="halfcheetah")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=300, help="K4 optimiser steps in the CPU sample")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------- helpers
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.proc, self.lines, self.gpu = None, [], gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        import torch.distributed as dist
+        th.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=th.device("cuda", local))
+    return rank, world, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    th.cuda.synchronize()
+
+
+def max_over_ranks(x, world):
+    if world > 1:
+        import torch.distributed as dist
+        t = th.tensor([x], dtype=th.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return x
+
+
+# --------------------------------------------------------------------------------------------- CPU baseline (oracle port)
+def cpu_iteration_estimate(w, k4_steps, seed=0):
+    """Times the oracle on a bounded sample of one ICRL iteration of workload `w` and extrapolates linearly.
+    K1 in the reference's per-env-step form (VecCostWrapper.step_wait: one [n_envs, .] call per step), K3 one full
+    rollout, K4 `k4_steps` optimiser steps of one rollout, K2 the full `backward_iters` (per-step IS via the O(N)
+    identity, i.e. *cheaper* than the reference's N x N broadcast)."""
+    from icrl_b200.learner import synth_demos, synth_rollouts
+    from oracle import cn as ocn, gae as ogae, ppo as oppo
+    th.manual_seed(seed)
+    T, E, n = w.n_steps, w.n_envs, w.n_steps * w.n_envs
+    small = type(w)(**{**w.__dict__, "rollouts": 1})
+    host = synth_rollouts(small, seed)
+    low = high = None
+    if not w.is_discrete:
+        low, high = -np.ones(w.act_dim, np.float32), np.ones(w.act_dim, np.float32)
+    spec = ocn.CNSpec(w.obs_dim, w.act_dim, w.cn_hidden, w.is_discrete, clip_obs=w.clip_obs, action_low=low, action_high=high,
+                      regularizer_coeff=w.cn_reg, per_step_importance_sampling=w.per_step_is)
+    dims = [spec.input_dims, *w.cn_hidden, 1]
+    cn_params = []
+    for i in range(len(dims) - 1):
+        lin = th.nn.Linear(dims[i], dims[i + 1])
+        cn_params += [lin.weight.detach().clone(), lin.bias.detach().clone()]
+    t = {}
+    # K1, per env step
+    calls = min(T, 512)
+    oo, aa = host["orig_obs"][0].astype(np.float64), host["actions"][0]
+    t0 = time.perf_counter()
+    costs = np.zeros((T, E), np.float32)
+    for s in range(calls):
+        costs[s] = ocn.cost_function(cn_params, spec, oo[s], aa[s])
+    t["k1"] = (time.perf_counter() - t0) / calls * T
+    costs = np.tile(costs[:calls], (T // calls + 1, 1))[:T].copy()
+    # K3
+    P = oppo.init_policy(w.obs_dim, w.act_dim, w.is_discrete)
+    obs_flat = th.tensor(host["obs"][0].reshape(n, w.obs_dim))
+    acts_flat = th.tensor(host["actions"][0].reshape(n, -1))
+    with th.no_grad():
+        v, cv, lp, _ = oppo.evaluate_actions(P, obs_flat, acts_flat.flatten() if w.is_discrete else acts_flat, w.is_discrete)
+    rv, cvv, lpp = (x.numpy().reshape(T, E) for x in (v, cv, lp))
+    t0 = time.perf_counter()
+    g = ogae.dual_gae(host["rewards"][0], rv, costs, cvv, host["dones"][0], rv[-1], cvv[-1], host["last_dones"][0], 0.99,
+                      w.reward_gae_lambda, 0.99, w.cost_gae_lambda)
+    t["k3"] = time.perf_counter() - t0
+    # K4
+    flat = {"observations": ogae.env_major(host["obs"][0]), "actions": ogae.env_major(host["actions"][0]),
+            "old_log_prob": ogae.env_major(lpp), "old_reward_values": ogae.env_major(rv),
+            "reward_advantages": ogae.env_major(g["reward_advantages"]), "reward_returns": ogae.env_major(g["reward_returns"]),
+            "old_cost_values": ogae.env_major(cvv), "cost_advantages": ogae.env_major(g["cost_advantages"]),
+            "cost_returns": ogae.env_major(g["cost_returns"])}
+    rs = np.random.RandomState(seed)
+    perms = [rs.permutation(n) for _ in range(w.n_epochs)]
+    adam = ocn.adam_init(list(P.values()))
+    steps_full = w.n_epochs * ((n + w.batch_size - 1) // w.batch_size)
+    k4_steps = min(k4_steps, steps_full)
+    t0 = time.perf_counter()
+    out = oppo.train(P, adam, flat, perms, is_discrete=w.is_discrete, batch_size=w.batch_size, n_epochs=w.n_epochs,
+                     lr=w.learning_rate, clip_range=w.clip_range, nu=w.penalty_initial_value, max_steps=k4_steps)
+    t["k4"] = (time.perf_counter() - t0) / out["steps"] * steps_full
+    # K2
+    t["k2"] = 0.0
+    if w.backward_iters > 0 and w.nominal_rows > 0:
+        eo, ea, no, na, lengths = synth_demos(w, seed)
+        t0 = time.perf_counter()
+        ocn.train(cn_params, ocn.adam_init(cn_params), spec, w.backward_iters, no, na, lengths, eo, ea, lr=w.cn_lr)
+        t["k2"] = time.perf_counter() - t0
+    est = w.rollouts * (t["k1"] + t["k3"] + t["k4"]) + t["k2"]
+    sample = (f"K1 {calls} of {T} per-step calls, K3 1 rollout, K4 {out['steps']} of {steps_full} optimiser steps of 1 rollout, "
+              f"K2 full ({w.backward_iters} iters); x{w.rollouts} rollouts, linear extrapolation")
+    return est, t, sample
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    th.set_num_threads(cores)
+    for _ in range(max(args.warmup, 1) - 1):
+        cpu_iteration_estimate(w, max(20, args.cpu_steps // 10))
+    ests, parts, sample = [], None, ""
+    t_wall = time.perf_counter()
+    for _ in range(max(args.steps, 1)):
+        est, parts, sample = cpu_iteration_estimate(w, args.cpu_steps)
+        ests.append(est)
+    est = float(np.mean(ests))
+    val = w.transitions_per_iteration / est
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": est * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w.name, "transitions_per_step": w.transitions_per_iteration, "early_stop": "disabled (fixed work)",
+                   "note": "host CPU only; time per ICRL iteration extrapolated from the bounded sample"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "seconds_per_part": {k: round(v, 4) for k, v in parts.items()},
+                         "sample_wall_s": round(time.perf_counter() - t_wall, 2)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# --------------------------------------------------------------------------------------------- e2e through the public API
+class _Env:
+    def __init__(self, w, n_envs):
+        from icrl_b200.learner import spaces_of
+        self.observation_space, self.action_space = spaces_of(w)
+        self.num_envs = n_envs
+
+
+class HostLearner:
+    """The same iteration through ConstraintNet / RolloutBufferWithCost / PPOLagrangian with numpy buffers."""
+
+    def __init__(self, w, dev_learner):
+        from icrl_b200.buffers import RolloutBufferWithCost
+        from icrl_b200.ppo_lag import PPOLagrangian
+        self.w, self.cn = w, dev_learner.cn
+        E = dev_learner.E
+        self.algo = PPOLagrangian("TwoCriticsMlpPolicy", _Env(w, E), n_steps=w.n_steps, batch_size=w.batch_size,
+                                  n_epochs=w.n_epochs, learning_rate=w.learning_rate, clip_range=w.clip_range,
+                                  reward_gae_lambda=w.reward_gae_lambda, cost_gae_lambda=w.cost_gae_lambda, target_kl=None,
+                                  penalty_initial_value=w.penalty_initial_value, penalty_learning_rate=w.penalty_learning_rate,
+                                  seed=0, device=dev_learner.dev)
+        host = dev_learner.host
+        self.bufs, self.pristine = [], []
+        for r in range(w.rollouts):
+            b = RolloutBufferWithCost(w.n_steps, self.algo.observation_space, self.algo.action_space, dev_learner.dev,
+                                      reward_gamma=0.99, reward_gae_lambda=w.reward_gae_lambda, cost_gamma=0.99,
+                                      cost_gae_lambda=w.cost_gae_lambda, n_envs=E)
+            b.observations[:], b.orig_observations[:], b.actions[:] = host["obs"][r], host["orig_obs"][r], host["actions"][r]
+            b.rewards[:], b.dones[:] = host["rewards"][r], host["dones"][r]
+            b.reward_values[:] = dev_learner.reward_values[r].cpu().numpy()
+            b.cost_values[:] = dev_learner.cost_values[r].cpu().numpy()
+            b.log_probs[:] = dev_learner.log_probs[r].cpu().numpy()
+            b.full, b.pos = True, w.n_steps
+            self.bufs.append(b)
+            self.pristine.append({k: getattr(b, k) for k in ("observations", "orig_observations", "actions", "log_probs",
+                                                              "reward_values", "cost_values")})
+        self.last_dones = host["last_dones"]
+        if w.nominal_rows:
+            from icrl_b200.learner import synth_demos
+            _, _, self.no, self.na, self.lengths = synth_demos(w, 0)
+        self.h2d = self.d2h = 0
+
+    def run(self):
+        w, n = self.w, self.w.n_steps * self.bufs[0].n_envs
+        h2d = d2h = 0
+        for r, b in enumerate(self.bufs):
+            for k, arr in self.pristine[r].items():   # "freshly collected" time-major arrays (train() rebinds env-major copies)
+                setattr(b, k, arr)
+            b.generator_ready = False
+            costs = self.cn.cost_function(b.orig_observations, b.actions)                      # K1
+            b.costs[:], b.orig_costs[:] = costs, costs
+            h2d += b.orig_observations.nbytes + b.actions.nbytes; d2h += costs.nbytes
+            b.compute_returns_and_advantage(b.reward_values[-1], b.cost_values[-1], self.last_dones[r])   # K3
+            h2d += 5 * n * 4 + 2 * b.n_envs * 4 + b.n_envs; d2h += 4 * n * 4
+            self.algo.rollout_buffer = b
+            self.algo.train()                                                                  # K4 + dual step
+            h2d += (b.observations.nbytes + b.actions.nbytes + 7 * n * 4) + w.n_epochs * n * 4 + 4
+            d2h += self.algo.last_train_stats.nbytes + 16 + 8
+        if w.backward_iters > 0 and w.nominal_rows > 0:
+            self.cn.train(w.backward_iters, self.no, self.na, self.lengths)                    # K2
+            h2d += self.no.nbytes + self.na.nbytes + (len(self.lengths) + 1) * 4; d2h += 18 * 4
+        self.h2d, self.d2h = h2d, d2h
+
+
+# --------------------------------------------------------------------------------------------- main (B200 arm)
+def time_steps(fn, steps, world, flush):
+    """Device time of exactly `steps` calls of fn, L2 flushed between calls (flush excluded), max over ranks."""
+    evs = [(th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier(world)
+    for s, e in evs:
+        flush.add_(1.0)                 # > L2 (126 MB) write: evicts the previous step's lines
+        s.record()
+        fn()
+        e.record()
+    barrier(world)
+    return max_over_ranks(sum(s.elapsed_time(e) for s, e in evs) * 1e-3, world)
+
+
+def kernel_roofline(learner, peak, peak_src):
+    """Dominant kernel = the persistent K4 launch: CUDA events around each of R launches on the launching stream."""
+    import ctypes as C
+    from icrl_b200 import _lib
+    w = learner.w
+    cfg, pol = learner.ppo_cfg(), learner.policy
+    times = []
+    for r in range(w.rollouts):
+        data = _lib.PpoData()
+        data.observations, data.actions = learner.data["obs"][r].data_ptr(), learner.data["actions"][r].data_ptr()
+        data.old_log_prob = learner.log_probs[r].data_ptr()
+        data.old_reward_values, data.old_cost_values = learner.reward_values[r].data_ptr(), learner.cost_values[r].data_ptr()
+        data.reward_advantages, data.reward_returns = learner.adv_r[r].data_ptr(), learner.ret_r[r].data_ptr()
+        data.cost_advantages, data.cost_returns = learner.adv_c[r].data_ptr(), learner.ret_c[r].data_ptr()
+        data.perm, data.nu_device = learner.perm[r].data_ptr(), learner.dual.nu.state[4:5].data_ptr()
+        s, e = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        s.record()
+        _lib.check(_lib.lib().icrl_ppo_train(C.byref(cfg), C.byref(data), _lib.ptr(pol._params), _lib.ptr(pol._adam_m),
+                                             _lib.ptr(pol._adam_v), pol.optimizer.step_count, _lib.ptr(learner.stats[r]),
+                                             _lib.ptr(learner.result[r]), _lib.current_stream()))
+        e.record()
+        pol.optimizer.step_count += learner.steps_taken_per_rollout()
+        th.cuda.synchronize()
+        times.append(s.elapsed_time(e) * 1e-3)
+    dur = float(np.mean(times))
+    steps = w.n_epochs * learner.steps_per_epoch
+    bytes_per_pass = (w.obs_dim + (1 if w.is_discrete else w.act_dim) + 7) * 4
+    alg_bytes = bytes_per_pass * learner.n * w.n_epochs
+    achieved = alg_bytes / dur / 1e9
+    return {"bound": "hbm", "kernel": "ppo_train_kernel (K4, persistent 3-CTA cluster)", "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "launch_ms": dur * 1e3, "optimiser_steps_per_launch": steps, "us_per_optimiser_step": dur / steps * 1e6,
+            "algorithmic_bytes_per_launch": alg_bytes,
+            "note": "1600 dependent optimiser steps on 64-128 rows each: latency-bound by construction (SURVEY §7), "
+                    "so the HBM fraction is tiny; us_per_optimiser_step is the figure of merit"}
+
+
+def family_rooflines(learner, peak):
+    """Per-family achieved HBM GB/s for the streaming kernels (K1 relabel, K3 GAE) at the workload's rollout size and at a
+    4M-transition sweep point (inputs > L2)."""
+    import ctypes as C
+    from icrl_b200 import _lib
+    w, L = learner.w, _lib.lib()
+    out = {}
+
+    def timeit(fn, reps=5):
+        fn(); th.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            s, e = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record(); th.cuda.synchronize()
+            ts.append(s.elapsed_time(e) * 1e-3)
+        return float(np.median(ts))
+
+    desc = learner.cn._get_desc()
+    k1_bytes_row = (learner.cn.input_dims + 1) * 4
+    for tag, T, E in (("rollout", w.n_steps, learner.E), ("sweep_4M", 2048, 2048)):
+        n = T * E
+        obs = th.randn(n, w.obs_dim, device=learner.dev)
+        acs = (th.randint(0, w.act_dim, (n,), device=learner.dev).float() if w.is_discrete
+               else th.randn(n, w.act_dim, device=learner.dev))
+        cost = th.empty(n, device=learner.dev)
+        d = timeit(lambda: _lib.check(L.icrl_cn_forward(C.byref(desc), _lib.ptr(obs), 0, _lib.ptr(acs), n, _lib.ptr(cost), 0,
+                                                        _lib.current_stream())))
+        out[f"k1_{tag}"] = {"rows": n, "us": d * 1e6, "GB/s": k1_bytes_row * n / d / 1e9, "frac_hbm": k1_bytes_row * n / d / 1e9 / peak}
+        arrs = [th.randn(T, E, device=learner.dev) for _ in range(4)] + [(th.rand(T, E, device=learner.dev) < 0.002).float()]
+        lv = [th.randn(E, device=learner.dev) for _ in range(2)] + [th.zeros(E, dtype=th.uint8, device=learner.dev)]
+        outs = [th.empty(T, E, device=learner.dev) for _ in range(4)]
+        d = timeit(lambda: _lib.check(L.icrl_dual_gae(*[_lib.ptr(x) for x in arrs + lv], T, E, 0.99, 0.95, 0.99, 0.95,
+                                                      *[_lib.ptr(o) for o in outs], _lib.current_stream())))
+        out[f"k3_{tag}"] = {"rows": n, "us": d * 1e6, "GB/s": 36 * n / d / 1e9, "frac_hbm": 36 * n / d / 1e9 / peak}
+    return out
+
+
+def main():
+    args = parse()
+    from icrl_b200.learner import WORKLOADS, DeviceLearner
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, w)
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    rank, world, local = dist_setup(args.gpus)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+    th.cuda.set_device(local)
+    from icrl_b200 import _lib
+    peak, peak_src = measured_peaks()
+    learner = DeviceLearner(w, seed=rank, device=th.device("cuda", local))
+    flush = th.zeros(64 * 1024 * 1024, device="cuda")      # 256 MB
+    for _ in range(args.warmup):
+        learner.run()
+    th.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.lib().icrl_launch_count()
+    t_dev = time_steps(learner.run, args.steps, world, flush)
+    launches = _lib.lib().icrl_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    per_step = t_dev / args.steps
+    total_tr = w.transitions_per_iteration * world
+    value = total_tr / per_step
+
+    e2e = None
+    if not args.no_e2e:
+        hl = HostLearner(w, learner)
+        for _ in range(2):
+            hl.run()
+        th.cuda.synchronize()
+        barrier(world)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            hl.run()
+        th.cuda.synchronize()
+        t_e2e = max_over_ranks(time.perf_counter() - t0, world) / args.steps
+        e2e = {"value": total_tr / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(hl.h2d), "d2h_bytes_per_step": int(hl.d2h),
+               "ms_per_step": t_e2e * 1e3, "path": "ConstraintNet.cost_function / RolloutBufferWithCost.compute_returns_and_advantage"
+               " / PPOLagrangian.train / ConstraintNet.train with numpy buffers (pinned staging + async H2D, D2H of costs, "
+               "advantages, per-step stats, metrics)"}
+
+    roof = fam = cpu = None
+    if rank == 0:
+        roof = kernel_roofline(learner, peak, peak_src)
+        fam = family_rooflines(learner, peak)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        th.set_num_threads(cores)
+        est, parts, sample = cpu_iteration_estimate(w, args.cpu_steps)
+        cpu = {"value": w.transitions_per_iteration / est, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+               "seconds_per_iteration_est": round(est, 2), "seconds_per_part": {k: round(v, 4) for k, v in parts.items()}}
+    barrier(world)
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": w.name, "transitions_per_step_per_gpu": w.transitions_per_iteration,
+                       "rollouts": w.rollouts, "n_steps": w.n_steps, "n_envs_per_gpu": w.n_envs, "batch_size": w.batch_size,
+                       "n_epochs": w.n_epochs, "backward_iters": w.backward_iters, "early_stop": "disabled (fixed work)",
+                       "l2": "flushed between timed steps (256 MB write, outside the timed region)",
+                       "parallelism": "1 GPU" if world == 1 else f"{world} independent learner replicas, one per GPU (no data-path "
+                                      "collective; see DESIGN.md multi-GPU)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "kernels": fam, "cpu_baseline": cpu}))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -58,7 +58,7 @@ class PpoCfg(C.Structure):
 class PpoData(C.Structure):
     _fields_ = [(n, c_void) for n in (
         "observations", "actions", "old_log_prob", "old_reward_values", "reward_advantages", "reward_returns",
-        "old_cost_values", "cost_advantages", "cost_returns", "perm")]
+        "old_cost_values", "cost_advantages", "cost_returns", "perm", "nu_device")]
 
 
 # name -> (restype, argtypes); every symbol include/icrl_b200.h declares (checked by tests/test_abi.py)

@@ -40,6 +40,7 @@ struct PpoArgs {
     int off_logstd, off_w1[3], off_b1[3], off_w2[3], off_b2[3], off_hw[3], off_hb[3];
     const float *obs, *act, *old_logp, *old_vr, *adv_r, *ret_r, *old_vc, *adv_c, *ret_c;
     const int* perm;
+    const float* nu_dev;
     float *params, *adam_m, *adam_v, *stats;
     int* result;
 };
@@ -174,6 +175,7 @@ __device__ __forceinline__ float adam_update(float p, float g, float& m, float& 
 template <int NT1>
 __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant__ PpoArgs a) {
     extern __shared__ __align__(16) float sm[];
+    const float nu = a.nu_dev ? *a.nu_dev : a.nu;
     const PpoSmem L = ppo_smem_layout(a.DP);
     const int tid = threadIdx.x;
     const int role = (int)cluster_ctarank();        // 0 pi, 1 vf, 2 cvf, >=3 idle (only joins the barriers)
@@ -497,10 +499,10 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                         if (pl1 < pl2) wgt = 1.f;
                         else if (pl1 > pl2) wgt = inrange ? 1.f : 0.f;
                         else wgt = 0.5f + (inrange ? 0.5f : 0.f);
-                        const float inv1pnu = 1.f / (1.f + a.nu);
+                        const float inv1pnu = 1.f / (1.f + nu);
                         float g = 0.f;
                         if (valid) {
-                            g = ratio * (-A_r * wgt + a.nu * A_c) * invB * inv1pnu;      // dL/dlogp
+                            g = ratio * (-A_r * wgt + nu * A_c) * invB * inv1pnu;      // dL/dlogp
                             if (hq == 0) {
                                 s_a += fminf(pl1, pl2);                                   // sum min(pl1, pl2)
                                 s_b += A_c * ratio;                                       // sum cost_adv * ratio
@@ -649,8 +651,8 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                 const float t_min = block_sum(s_a, scratch), t_cr = block_sum(s_b, scratch), t_clip = block_sum(s_c, scratch),
                             t_kl = block_sum(s_d, scratch), t_ent = block_sum(s_e, scratch);
                 float pl = -(t_min * invB);
-                pl = pl + a.nu * (t_cr * invB);
-                pl = pl / (1.f + a.nu);
+                pl = pl + nu * (t_cr * invB);
+                pl = pl / (1.f + nu);
                 kl_step = t_kl * invB;
                 if (tid == 0) {
                     a.stats[so + 0] = pl;
@@ -984,6 +986,7 @@ int icrl_ppo_train(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* pa
     a.old_vc = data->old_cost_values ? data->old_cost_values : data->cost_returns;
     a.adv_c = data->cost_advantages; a.ret_c = data->cost_returns;
     a.perm = data->perm;
+    a.nu_dev = data->nu_device;
     a.params = params; a.adam_m = adam_m; a.adam_v = adam_v; a.stats = step_stats; a.result = result;
     a.step_before = adam_step_before;
     const int n_tiles = 16 * (a.DP / 4);

@@ -181,6 +181,8 @@ typedef struct icrl_ppo_data {
     const float* cost_advantages;   /* [T,E] */
     const float* cost_returns;      /* [T,E] */
     const int32_t* perm;            /* [n_epochs, T*E] */
+    const float* nu_device;         /* optional: read the penalty nu from this device float instead of cfg->nu
+                                       (lets a device-resident dual state feed the next launch without a host read) */
 } icrl_ppo_data;
 
 #define ICRL_PPO_STATS_PER_STEP 8
