@@ -51,6 +51,20 @@ __device__ __forceinline__ Step gae_step(const float* __restrict__ rew, const fl
     return s;
 }
 
+constexpr int UB = 8;   // time steps whose loads are batched
+
+// both signals' (delta, coef) at time t for column col
+__device__ __forceinline__ void load_steps(const GaeArgs& a, int t, int col, float lvr, float lvc, double alive_last,
+                                           Step& sr, Step& sc) {
+    const int64_t idx = (int64_t)t * a.E + col;
+    const bool last = (t == a.T - 1);
+    const float alive = last ? 0.f : __fsub_rn(1.0f, a.dones[idx + a.E]);
+    const float nvr = last ? lvr : a.vr[idx + a.E];
+    const float nvc = last ? lvc : a.vc[idx + a.E];
+    sr = gae_step(a.r, a.vr, nvr, alive, last, alive_last, a.g_r, a.gl_r, idx);
+    sc = gae_step(a.c, a.vc, nvc, alive, last, alive_last, a.g_c, a.gl_c, idx);
+}
+
 template <int NW>
 __global__ void __launch_bounds__(NW * 32) dual_gae_kernel(const GaeArgs a) {
     __shared__ double sM[2][NW][32], sB[2][NW][32];
@@ -69,21 +83,26 @@ __global__ void __launch_bounds__(NW * 32) dual_gae_kernel(const GaeArgs a) {
         lvc = a.last_vc[col];
     }
 
-    // ---- phase 1: fold the chunk
+    // ---- phase 1: fold the chunk.  Loads of UB consecutive steps are issued together (the recurrence itself is
+    // serial, the memory traffic must not be), then folded in order.
     double Mr = 1.0, Br = 0.0, Mc = 1.0, Bc = 0.0;
     if (active) {
-        for (int t = hi - 1; t >= lo; --t) {
-            const int64_t idx = (int64_t)t * E + col;
-            const bool last = (t == T - 1);
-            const float alive = last ? 0.f : __fsub_rn(1.0f, a.dones[idx + E]);
-            const float nvr = last ? lvr : a.vr[idx + E];
-            const float nvc = last ? lvc : a.vc[idx + E];
-            const Step sr = gae_step(a.r, a.vr, nvr, alive, last, alive_last, a.g_r, a.gl_r, idx);
-            const Step sc = gae_step(a.c, a.vc, nvc, alive, last, alive_last, a.g_c, a.gl_c, idx);
-            Br = sr.delta + sr.coef * Br;
-            Mr = sr.coef * Mr;
-            Bc = sc.delta + sc.coef * Bc;
-            Mc = sc.coef * Mc;
+        for (int t1 = hi - 1; t1 >= lo; t1 -= UB) {
+            Step sr[UB], sc[UB];
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int t = t1 - u;
+                if (t >= lo) load_steps(a, t, col, lvr, lvc, alive_last, sr[u], sc[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                if (t1 - u >= lo) {
+                    Br = sr[u].delta + sr[u].coef * Br;
+                    Mr = sr[u].coef * Mr;
+                    Bc = sc[u].delta + sc[u].coef * Bc;
+                    Mc = sc[u].coef * Mc;
+                }
+            }
         }
     }
     sM[0][w][lane] = Mr; sB[0][w][lane] = Br;
@@ -99,21 +118,32 @@ __global__ void __launch_bounds__(NW * 32) dual_gae_kernel(const GaeArgs a) {
 
     // ---- phase 3: replay with the reference's rounding, store
     if (!active) return;
-    for (int t = hi - 1; t >= lo; --t) {
-        const int64_t idx = (int64_t)t * E + col;
-        const bool last = (t == T - 1);
-        const float alive = last ? 0.f : __fsub_rn(1.0f, a.dones[idx + E]);
-        const float nvr = last ? lvr : a.vr[idx + E];
-        const float nvc = last ? lvc : a.vc[idx + E];
-        const Step sr = gae_step(a.r, a.vr, nvr, alive, last, alive_last, a.g_r, a.gl_r, idx);
-        const Step sc = gae_step(a.c, a.vc, nvc, alive, last, alive_last, a.g_c, a.gl_c, idx);
-        carry_r = __dadd_rn(sr.delta, __dmul_rn(sr.coef, carry_r));
-        carry_c = __dadd_rn(sc.delta, __dmul_rn(sc.coef, carry_c));
-        const float ar = (float)carry_r, ac = (float)carry_c;
-        a.adv_r[idx] = ar;
-        a.adv_c[idx] = ac;
-        a.ret_r[idx] = __fadd_rn(ar, a.vr[idx]);
-        a.ret_c[idx] = __fadd_rn(ac, a.vc[idx]);
+    for (int t1 = hi - 1; t1 >= lo; t1 -= UB) {
+        Step sr[UB], sc[UB];
+        float vr[UB], vc[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            const int t = t1 - u;
+            if (t >= lo) {
+                load_steps(a, t, col, lvr, lvc, alive_last, sr[u], sc[u]);
+                vr[u] = a.vr[(int64_t)t * E + col];
+                vc[u] = a.vc[(int64_t)t * E + col];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            const int t = t1 - u;
+            if (t >= lo) {
+                const int64_t idx = (int64_t)t * E + col;
+                carry_r = __dadd_rn(sr[u].delta, __dmul_rn(sr[u].coef, carry_r));
+                carry_c = __dadd_rn(sc[u].delta, __dmul_rn(sc[u].coef, carry_c));
+                const float ar = (float)carry_r, ac = (float)carry_c;
+                a.adv_r[idx] = ar;
+                a.adv_c[idx] = ac;
+                a.ret_r[idx] = __fadd_rn(ar, vr[u]);
+                a.ret_c[idx] = __fadd_rn(ac, vc[u]);
+            }
+        }
     }
 }
 
@@ -123,7 +153,7 @@ int dual_gae_device(const GaeArgs& a, cudaStream_t st) {
     // more warps along time when there are few columns (latency), fewer when the grid already fills the GPU
     const int64_t work = (int64_t)a.T * a.E;
     if (a.T >= 1024 && grid < 4 * sm_count()) {
-        dual_gae_kernel<32><<<grid, 32 * 32, 0, st>>>(a);
+        dual_gae_kernel<16><<<grid, 16 * 32, 0, st>>>(a);
     } else if (a.T >= 256 && work < ((int64_t)1 << 26)) {
         dual_gae_kernel<8><<<grid, 8 * 32, 0, st>>>(a);
     } else if (a.T >= 64) {

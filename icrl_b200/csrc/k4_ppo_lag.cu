@@ -40,6 +40,8 @@ struct PpoArgs {
     int off_logstd, off_w1[3], off_b1[3], off_w2[3], off_b2[3], off_hw[3], off_hb[3];
     const float *obs, *act, *old_logp, *old_vr, *adv_r, *ret_r, *old_vc, *adv_c, *ret_c;
     const int* perm;
+    const int* poff;          // perm translated to time-major element offsets (prologue kernel)
+    const float* advstats;    // [steps][4]: mean(adv_r), std(adv_r) (unbiased), mean(adv_c) per minibatch
     const float* nu_dev;
     float *params, *adam_m, *adam_v, *stats;
     int* result;
@@ -64,6 +66,12 @@ __device__ __forceinline__ void st_remote_f32(float* local_ptr, uint32_t rank, f
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
 }
+
+__device__ __forceinline__ void cp_async_4(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // ---------------------------------------------------------------- block reductions (NTH threads)
 __device__ __forceinline__ float block_sum(float v, float* scratch) {
@@ -102,15 +110,15 @@ __host__ __device__ inline PpoSmem ppo_smem_layout(int DP) {
     s.hw = o; o += AMAX * WA_LD;
     s.hb = o; o += AMAX;
     s.logstd = o; o += AMAX;
-    s.x = o; o += RB * DP;
+    s.x = o; o += 2 * RB * DP;      // double buffered (cp.async prefetch of the next chunk)
     s.h1 = o; o += RB * H;
     s.h2 = o; o += RB * H;
     s.dh = o; o += RB * H;
-    s.rowf = o; o += RB * 8;        // per-row scalars: 0 old_logp, 1 adv_r~, 2 adv_c~, 3 target return, 4 old value, 5 g/dV
+    s.rowf = o; o += 2 * RB * 8;      // per-row scalars: 0 old_logp, 1 adv_r~, 2 adv_c~, 3 target return, 4 old value, 5 g/dV
     s.dmean = o; o += RB * AMAX;
-    s.act = o; o += RB * AMAX;
+    s.act = o; o += 2 * RB * AMAX;
     s.mu = o; o += RB * AMAX;        // action-head outputs (means / logits)
-    s.rowoff = o; o += RB;           // int: time-major element offset t*E+e of each chunk row (-1 = padding)
+    s.rowoff = o; o += 3 * RB;       // int: 3-deep ring of chunk row offsets t*E+e (-1 = padding)
     s.scratch = o; o += 64;         // 32 floats / 16 doubles of reduction scratch (8-byte aligned: o is even)
     s.xch = o; o += 2 * 4 * 2;      // [parity][rank][{sumsq, stop}]
     s.total_bytes = o * 4;
@@ -118,24 +126,29 @@ __host__ __device__ inline PpoSmem ppo_smem_layout(int DP) {
 }
 
 // 64x64 += A[64 x K] * Bt[K x 64]  (A row-major lda, Bt k-major ld 64); thread tile rows 4ty.., cols 4tx..
+// KC > 0: compile-time K (fully unrolled so operand loads run ahead of the FMAs); KC == 0: runtime K.
+template <int KC>
 __device__ __forceinline__ void gemm_tile_4x4(float (&acc)[4][4], const float* __restrict__ A, int lda,
                                               const float* __restrict__ Bt, int K, int ty, int tx) {
     const float* a0 = A + (4 * ty) * lda;
     const float* b0 = Bt + 4 * tx;
-    for (int k = 0; k < K; k += 4) {
-        float4 a[4];
+    const int kend = KC > 0 ? KC : K;
+#pragma unroll (KC > 0 ? KC / 4 : 2)
+    for (int k = 0; k < kend; k += 4) {
+        float4 a[4], w[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + i * lda + k);
 #pragma unroll
+        for (int kk = 0; kk < 4; ++kk) w[kk] = *reinterpret_cast<const float4*>(b0 + (k + kk) * H);
+#pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-            const float4 w = *reinterpret_cast<const float4*>(b0 + (k + kk) * H);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
-                acc[i][0] = fmaf(av, w.x, acc[i][0]);
-                acc[i][1] = fmaf(av, w.y, acc[i][1]);
-                acc[i][2] = fmaf(av, w.z, acc[i][2]);
-                acc[i][3] = fmaf(av, w.w, acc[i][3]);
+                acc[i][0] = fmaf(av, w[kk].x, acc[i][0]);
+                acc[i][1] = fmaf(av, w[kk].y, acc[i][1]);
+                acc[i][2] = fmaf(av, w[kk].z, acc[i][2]);
+                acc[i][3] = fmaf(av, w[kk].w, acc[i][3]);
             }
         }
     }
@@ -143,11 +156,11 @@ __device__ __forceinline__ void gemm_tile_4x4(float (&acc)[4][4], const float* _
 
 // acc[jj][kk] += sum_r L[r][4tj+jj] * R[r][4tk+kk]   (both row-major; reduction over the chunk's rows)
 __device__ __forceinline__ void outer_tile_4x4(float (&acc)[4][4], const float* __restrict__ L, int ldl,
-                                               const float* __restrict__ R, int ldr, int rows, int tj, int tk) {
+                                               const float* __restrict__ R, int ldr, int tj, int tk) {
     const float* l0 = L + 4 * tj;
     const float* r0 = R + 4 * tk;
-#pragma unroll 4
-    for (int r = 0; r < rows; ++r) {
+#pragma unroll 8
+    for (int r = 0; r < RB; ++r) {      // padding rows of the chunk hold zero gradients, so the trip count is fixed
         const float4 d = *reinterpret_cast<const float4*>(l0 + r * ldl);
         const float4 h = *reinterpret_cast<const float4*>(r0 + r * ldr);
         acc[0][0] = fmaf(d.x, h.x, acc[0][0]); acc[0][1] = fmaf(d.x, h.y, acc[0][1]);
@@ -163,13 +176,60 @@ __device__ __forceinline__ void outer_tile_4x4(float (&acc)[4][4], const float* 
 
 // one Adam update in torch's single-tensor form (torch/optim/adam.py); returns the new parameter
 struct AdamConsts {
-    float one_minus_b1, b2, one_minus_b2, bc2_sqrt, eps, neg_step_size;
+    float one_minus_b1, b2, one_minus_b2, inv_bc2_sqrt, eps, neg_step_size;
 };
 __device__ __forceinline__ float adam_update(float p, float g, float& m, float& v, const AdamConsts& c) {
     m = fmaf(c.one_minus_b1, g - m, m);                        // exp_avg.lerp_(grad, 1 - beta1)
     v = fmaf(c.one_minus_b2 * g, g, v * c.b2);                 // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
-    const float denom = sqrtf(v) / c.bc2_sqrt + c.eps;         // (sqrt(v) / sqrt(bc2)).add_(eps)
-    return fmaf(c.neg_step_size, m / denom, p);                // param.addcdiv_(m, denom, value=-step_size)
+    // (sqrt(v) / sqrt(bc2)).add_(eps); param.addcdiv_(m, denom, value=-step_size).  The two divisions are done as a
+    // multiply by the precomputed reciprocal and a 2-ulp fast division: <= 3e-7 relative on an lr-sized update.
+    const float denom = fmaf(sqrtf(v), c.inv_bc2_sqrt, c.eps);
+    return fmaf(c.neg_step_size, __fdividef(m, denom), p);
+}
+
+// ---------------------------------------------------------------- prologue: one CTA per optimiser step
+// (i) numpy's env-major minibatch indices (row = e*T + t, buffers.py:52-65) -> time-major element offsets t*E + e,
+// (ii) the minibatch statistics of ppo_lag.py:218-222: mean and unbiased std of the reward advantages, mean of the cost
+// advantages (float64 accumulation like ATen's CPU reductions).  They depend only on data, never on parameters, so all
+// 1 600 of them are computed in parallel here instead of inside the dependent step chain.
+__global__ void __launch_bounds__(128) ppo_prologue_kernel(const int* __restrict__ perm, int* __restrict__ poff,
+                                                           float* __restrict__ advstats, const float* __restrict__ adv_r,
+                                                           const float* __restrict__ adv_c, int T, int E, int N, int B,
+                                                           int spe) {
+    __shared__ double red[2][4];
+    const int step = blockIdx.x, epoch = step / spe, mb = step - epoch * spe;
+    const int Bn = min(B, N - mb * B);
+    const size_t base = (size_t)epoch * N + (size_t)mb * B;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double sr = 0.0, sc = 0.0;
+    for (int i = tid; i < Bn; i += blockDim.x) {
+        const int row = perm[base + i], t = row % T, e = row / T, o = t * E + e;
+        poff[base + i] = o;
+        sr += (double)adv_r[o];
+        sc += (double)adv_c[o];
+    }
+    sr = warp_sum(sr); sc = warp_sum(sc);
+    if (lane == 0) { red[0][warp] = sr; red[1][warp] = sc; }
+    __syncthreads();
+    const double mr = (red[0][0] + red[0][1] + red[0][2] + red[0][3]) / Bn;
+    const double mc = (red[1][0] + red[1][1] + red[1][2] + red[1][3]) / Bn;
+    __syncthreads();
+    double ssq = 0.0;
+    for (int i = tid; i < Bn; i += blockDim.x) {
+        const int row = perm[base + i], t = row % T, e = row / T;
+        const double dv = (double)adv_r[t * E + e] - mr;
+        ssq += dv * dv;
+    }
+    ssq = warp_sum(ssq);
+    if (lane == 0) red[0][warp] = ssq;
+    __syncthreads();
+    if (tid == 0) {
+        const double tot = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+        advstats[step * 4 + 0] = (float)mr;
+        advstats[step * 4 + 1] = (float)sqrt(tot / (double)(Bn - 1));
+        advstats[step * 4 + 2] = (float)mc;
+        advstats[step * 4 + 3] = 0.f;
+    }
 }
 
 template <int NT1>
@@ -191,8 +251,8 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
     float* LOGSTD = sm + L.logstd;
     float* X = sm + L.x; float* H1 = sm + L.h1; float* H2 = sm + L.h2; float* DH = sm + L.dh;
     float* ROWF = sm + L.rowf; float* DMEAN = sm + L.dmean; float* ACT = sm + L.act; float* MU = sm + L.mu;
-    int* ROWOFF = reinterpret_cast<int*>(sm + L.rowoff);
-    float* scratch = sm + L.scratch; double* dscratch = reinterpret_cast<double*>(sm + L.scratch);
+    int* IDX = reinterpret_cast<int*>(sm + L.rowoff);
+    float* scratch = sm + L.scratch;
     float* XCH = sm + L.xch;
 
     // ---- thread -> parameter ownership (fixed for the whole launch)
@@ -228,6 +288,9 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
     if (tid < H) { B1[tid] = 0.f; B2[tid] = 0.f; }
     if (tid < AMAX) { HB[tid] = 0.f; LOGSTD[tid] = 0.f; }
     if (tid < 16) XCH[tid] = 0.f;
+    for (int i = tid; i < 2 * RB * DP; i += NTH) X[i] = 0.f;     // padding columns k in [D, DP) stay zero forever
+    for (int i = tid; i < 2 * RB * 8; i += NTH) ROWF[i] = 0.f;
+    for (int i = tid; i < 2 * RB * AMAX; i += NTH) ACT[i] = 0.f;
     __syncthreads();
     if (working) {
 #pragma unroll
@@ -277,6 +340,83 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
     double b1_pow = pow(a.beta1, (double)a.step_before), b2_pow = pow(a.beta2, (double)a.step_before);
     const int ty = tid >> 4, tx = tid & 15;     // forward tile: rows 4ty.., cols 4tx..
     const int hr = tid >> 2, hq = tid & 3;      // head mapping: row hr, quarter hq
+    const int warp = tid >> 5, lane = tid & 31;
+    const int aw = a.is_discrete ? 1 : a.A;
+
+    // ---- chunk pipeline: the (epoch, minibatch, 64-row chunk) sequence is known up front (the prologue kernel turned
+    // numpy's permutations into time-major element offsets), so chunk q+1's rows are gathered with cp.async while chunk q
+    // is being computed, and chunk q+2's offsets are fetched one stage earlier still.  No global latency is exposed.
+    struct Cursor { int epoch, mb, c0; };
+    auto cur_valid = [&](const Cursor& c) { return c.epoch < a.n_epochs; };
+    auto cur_bn = [&](const Cursor& c) { return min(a.B, a.N - c.mb * a.B); };
+    auto cur_rows = [&](const Cursor& c) { return min(RB, cur_bn(c) - c.c0); };
+    auto cur_next = [&](Cursor c) {
+        c.c0 += RB;
+        if (c.c0 >= cur_bn(c)) { c.c0 = 0; if (++c.mb >= a.steps_per_epoch) { c.mb = 0; ++c.epoch; } }
+        return c;
+    };
+    auto prefetch_idx = [&](const Cursor& c, int slot) {          // offsets of the chunk's rows -> IDX[slot] (-1 = padding)
+        if (tid < RB) {
+            int* dst = IDX + slot * RB + tid;
+            if (cur_valid(c) && tid < cur_rows(c))
+                cp_async_4(dst, a.poff + (size_t)c.epoch * a.N + (size_t)c.mb * a.B + c.c0 + tid);
+            else
+                *dst = -1;
+        }
+    };
+    auto prefetch_data = [&](int slot, int buf) {                 // gather the rows named by IDX[slot] into buffer `buf`
+        const int* offs = IDX + slot * RB;
+        float* Xb = X + buf * RB * DP;
+        for (int r = warp; r < RB; r += NTH / 32) {
+            const int o = offs[r];
+            if (o >= 0) {
+                const float* src = a.obs + (size_t)o * D;
+                for (int k = lane; k < D; k += 32) cp_async_4(Xb + r * DP + k, src + k);
+            } else {
+                for (int k = lane; k < D; k += 32) Xb[r * DP + k] = 0.f;
+            }
+        }
+        float* Rb = ROWF + buf * RB * 8;
+        if (tid < RB) {
+            const int o = offs[tid];
+            if (o >= 0) {
+                if (role == 0) {
+                    cp_async_4(Rb + tid * 8 + 0, a.old_logp + o);
+                    cp_async_4(Rb + tid * 8 + 1, a.adv_r + o);
+                    cp_async_4(Rb + tid * 8 + 2, a.adv_c + o);
+                } else if (role == 1) {
+                    cp_async_4(Rb + tid * 8 + 3, a.ret_r + o);
+                    cp_async_4(Rb + tid * 8 + 4, a.old_vr + o);
+                } else {
+                    cp_async_4(Rb + tid * 8 + 3, a.ret_c + o);
+                    cp_async_4(Rb + tid * 8 + 4, a.old_vc + o);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 5; ++i) Rb[tid * 8 + i] = 0.f;
+            }
+        }
+        if (role == 0) {
+            float* Ab = ACT + buf * RB * AMAX;
+            const int r = tid >> 2, o = offs[r];
+            for (int d = tid & 3; d < aw; d += 4) {
+                if (o >= 0) cp_async_4(Ab + r * AMAX + d, a.act + (size_t)o * aw + d);
+                else Ab[r * AMAX + d] = 0.f;
+            }
+        }
+    };
+
+    Cursor cur = {0, 0, 0};
+    int q = 0;                                   // running chunk counter (buffer / slot parity)
+    if (working) {
+        prefetch_idx(cur, 0);
+        prefetch_idx(cur_next(cur), 1);
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncthreads();
+        prefetch_data(0, 0);
+        cp_async_commit();
+    }
 
     int step = 0, early_stop_epoch = a.n_epochs;
     double epoch_kl_sum = 0.0;
@@ -287,7 +427,6 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
         int epoch_steps = 0;
         for (int mb = 0; mb < a.steps_per_epoch && !stop_all; ++mb, ++step) {
             const int parity = step & 1;
-            const int* idx = a.perm + (size_t)epoch * a.N + (size_t)mb * a.B;
             const int Bn = min(a.B, a.N - mb * a.B);
             const float invB = 1.0f / (float)Bn;
 
@@ -303,82 +442,28 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                     for (int n = 0; n < NT1; ++n) g_w1[n][i][j] = 0.f;
                 }
             }
-            // loss partial sums (thread-local, reduced at the end of the step)
+            // loss partial sums (thread-local, one merged block reduction at the end of the step)
             float s_a = 0.f, s_b = 0.f, s_c = 0.f, s_d = 0.f, s_e = 0.f;
-            float adv_mean_r = 0.f, adv_rstd_r = 1.f, adv_mean_c = 0.f;
-
-            if (role == 0) {
-                // minibatch statistics of the advantages (ppo_lag.py:218-222): mean, unbiased std (float64 accumulate
-                // like ATen's CPU reductions), cost advantages only centred.
-                double sr = 0.0, sc = 0.0;
-                for (int i = tid; i < Bn; i += NTH) {
-                    const int row = idx[i], t = row % a.T, e = row / a.T;
-                    const size_t o = (size_t)t * a.E + e;
-                    sr += (double)a.adv_r[o];
-                    sc += (double)a.adv_c[o];
-                }
-                sr = block_sum(sr, dscratch);
-                sc = block_sum(sc, dscratch);
-                const double mr = sr / Bn;
-                adv_mean_r = (float)mr;
-                adv_mean_c = (float)(sc / Bn);
-                double ssq = 0.0;
-                for (int i = tid; i < Bn; i += NTH) {
-                    const int row = idx[i], t = row % a.T, e = row / a.T;
-                    const double dv = (double)a.adv_r[(size_t)t * a.E + e] - mr;
-                    ssq += dv * dv;
-                }
-                ssq = block_sum(ssq, dscratch);
-                adv_rstd_r = (float)sqrt(ssq / (double)(Bn - 1));   // std(); used as x / (std + 1e-8)
-            }
+            // minibatch statistics of the advantages (ppo_lag.py:218-222) from the prologue kernel's table
+            const float adv_mean_r = a.advstats[step * 4 + 0], adv_std_r = a.advstats[step * 4 + 1],
+                        adv_mean_c = a.advstats[step * 4 + 2];
 
             if (working) {
-                for (int c0 = 0; c0 < Bn; c0 += RB) {
+                for (int c0 = 0; c0 < Bn; c0 += RB, ++q) {
                     const int rows = min(RB, Bn - c0);
-                    __syncthreads();
-                    // ---- gather the chunk: row offsets first, then obs rows (+ per-row scalars, actions)
-                    if (tid < RB) {
-                        int o = -1;
-                        if (tid < rows) {
-                            const int row = idx[c0 + tid], t = row % a.T, e = row / a.T;
-                            o = t * a.E + e;
-                        }
-                        ROWOFF[tid] = o;
-                    }
-                    __syncthreads();
+                    const int buf = q & 1;
+                    const float* Xc = X + buf * RB * DP;
+                    float* Rc = ROWF + buf * RB * 8;
+                    const float* Ac = ACT + buf * RB * AMAX;
+                    cp_async_wait_all();
+                    __syncthreads();          // chunk q landed (and everybody is done with chunk q-1's buffers)
                     {
-                        const int warp = tid >> 5, lane = tid & 31;
-                        for (int r = warp; r < RB; r += NTH / 32) {
-                            const int o = ROWOFF[r];
-                            const float* src = a.obs + (size_t)(o < 0 ? 0 : o) * D;
-                            for (int k = lane; k < DP; k += 32) X[r * DP + k] = (o >= 0 && k < D) ? src[k] : 0.f;
-                        }
+                        const Cursor nxt = cur_next(cur);
+                        if (cur_valid(nxt)) prefetch_data((q + 1) % 3, buf ^ 1);
+                        prefetch_idx(cur_next(nxt), (q + 2) % 3);
+                        cp_async_commit();
+                        cur = nxt;
                     }
-                    if (tid < RB) {
-                        const int r = tid, o = ROWOFF[r];
-                        float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f, f4 = 0.f;
-                        if (o >= 0) {
-                            if (role == 0) {
-                                f0 = a.old_logp[o];
-                                f1 = (a.adv_r[o] - adv_mean_r) / (adv_rstd_r + 1e-8f);
-                                f2 = a.adv_c[o] - adv_mean_c;
-                            } else if (role == 1) {
-                                f3 = a.ret_r[o]; f4 = a.old_vr[o];
-                            } else {
-                                f3 = a.ret_c[o]; f4 = a.old_vc[o];
-                            }
-                        }
-                        ROWF[r * 8 + 0] = f0; ROWF[r * 8 + 1] = f1; ROWF[r * 8 + 2] = f2;
-                        ROWF[r * 8 + 3] = f3; ROWF[r * 8 + 4] = f4;
-                    }
-                    if (role == 0) {
-                        const int aw = a.is_discrete ? 1 : a.A;
-                        const int r = tid >> 2;
-                        const int o = ROWOFF[r];
-                        for (int d = tid & 3; d < AMAX; d += 4)
-                            ACT[r * AMAX + d] = (o >= 0 && d < aw) ? a.act[(size_t)o * aw + d] : 0.f;
-                    }
-                    __syncthreads();
 
                     // ---- forward layer 1: H1 = tanh(X W1^T + b1)
                     {
@@ -387,7 +472,7 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                         for (int i = 0; i < 4; ++i)
 #pragma unroll
                             for (int j = 0; j < 4; ++j) acc[i][j] = B1[4 * tx + j];
-                        gemm_tile_4x4(acc, X, DP, W1t, DP, ty, tx);
+                        gemm_tile_4x4<0>(acc, Xc, DP, W1t, DP, ty, tx);
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
                             *reinterpret_cast<float4*>(H1 + (4 * ty + i) * H + 4 * tx) =
@@ -401,7 +486,7 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                         for (int i = 0; i < 4; ++i)
 #pragma unroll
                             for (int j = 0; j < 4; ++j) acc[i][j] = B2[4 * tx + j];
-                        gemm_tile_4x4(acc, H1, H, W2t, H, ty, tx);
+                        gemm_tile_4x4<H>(acc, H1, H, W2t, H, ty, tx);
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
                             *reinterpret_cast<float4*>(H2 + (4 * ty + i) * H + 4 * tx) =
@@ -443,7 +528,7 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                                 if (d < a.A) {
                                     const float sigma = expf(LOGSTD[d]);
                                     const float var = sigma * sigma, log_scale = logf(sigma);
-                                    const float diff = ACT[hr * AMAX + d] - out[u];
+                                    const float diff = Ac[hr * AMAX + d] - out[u];
                                     lp += -(diff * diff) / (2.f * var) - log_scale - LOG_SQRT_2PI;
                                     en += HALF_LOG_2PI_PLUS_HALF + log_scale;
                                     dcoef[u] = diff / var;
@@ -463,7 +548,7 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                             for (int u = 0; u < 4; ++u) if (hq + 4 * u < a.A) se += expf(out[u] - mx);
                             se += __shfl_xor_sync(0xffffffffu, se, 1); se += __shfl_xor_sync(0xffffffffu, se, 2);
                             const float lse = mx + logf(se);
-                            const int ai = (int)ACT[hr * AMAX + 0];
+                            const int ai = (int)Ac[hr * AMAX + 0];
                             float lp = 0.f, en = 0.f, pr[4], lg[4];
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
@@ -488,8 +573,10 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                                 }
                             }
                         }
-                        // surrogate (ppo_lag.py:225-236)
-                        const float old_lp = ROWF[hr * 8 + 0], A_r = ROWF[hr * 8 + 1], A_c = ROWF[hr * 8 + 2];
+                        // surrogate (ppo_lag.py:218-236); advantages normalised here with the minibatch statistics
+                        const float old_lp = Rc[hr * 8 + 0];
+                        const float A_r = (Rc[hr * 8 + 1] - adv_mean_r) / (adv_std_r + 1e-8f);
+                        const float A_c = Rc[hr * 8 + 2] - adv_mean_c;
                         const float ratio = expf(logp - old_lp);
                         const float lo = 1.f - a.clip_range, hi = 1.f + a.clip_range;
                         const float clipped = fminf(fmaxf(ratio, lo), hi);
@@ -517,7 +604,7 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                             const int d = hq + 4 * u;
                             if (d < AMAX) DMEAN[hr * AMAX + d] = (d < a.A) ? (g * dcoef[u] + ge * dent[u]) : 0.f;
                         }
-                        if (hq == 0) ROWF[hr * 8 + 5] = g;
+                        if (hq == 0) Rc[hr * 8 + 5] = g;
                     } else {
                         // value head: partial dot over k in [16hq, 16hq+16)
                         float acc = 0.f;
@@ -532,7 +619,7 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
                         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
                         const float V = acc + HB[0];
-                        const float target = ROWF[hr * 8 + 3], oldv = ROWF[hr * 8 + 4];
+                        const float target = Rc[hr * 8 + 3], oldv = Rc[hr * 8 + 4];
                         const bool clipvf = (role == 1) ? a.has_clip_vf_r : a.has_clip_vf_c;
                         const float cr = (role == 1) ? a.clip_vf_r : a.clip_vf_c;
                         float Vp = V, pass = 1.f;
@@ -552,11 +639,11 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                     }
                     __syncthreads();
 
-                    // ---- head weight / bias / log_std gradients
+                    // ---- head weight / bias / log_std gradients (rows beyond `rows` carry zero dmean: loops run over RB)
                     if (hd < AOUT) {
                         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-#pragma unroll 4
-                        for (int r = 0; r < rows; ++r) {
+#pragma unroll 8
+                        for (int r = 0; r < RB; ++r) {
                             const float dm = DMEAN[r * AMAX + hd];
                             const float4 h = *reinterpret_cast<const float4*>(H2 + r * H + 4 * hk4);
                             acc0 = fmaf(dm, h.x, acc0); acc1 = fmaf(dm, h.y, acc1);
@@ -566,16 +653,18 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                     }
                     if (s_kind == 2) {
                         float acc = 0.f;
-                        for (int r = 0; r < rows; ++r) acc += DMEAN[r * AMAX + s_idx];
+#pragma unroll 8
+                        for (int r = 0; r < RB; ++r) acc += DMEAN[r * AMAX + s_idx];
                         g_s += acc;
                     } else if (s_kind == 3) {
                         // d logp / d log_std_d = diff^2/var - 1 ; entropy: d(-mean H)/d log_std = -1
                         const float sigma = expf(LOGSTD[s_idx]);
-                        const float var = sigma * sigma;
+                        const float inv_var = 1.f / (sigma * sigma);
                         float acc = 0.f;
-                        for (int r = 0; r < rows; ++r) {
-                            const float diff = ACT[r * AMAX + s_idx] - MU[r * AMAX + s_idx];
-                            acc = fmaf(ROWF[r * 8 + 5], diff * diff / var - 1.f, acc);
+#pragma unroll 8
+                        for (int r = 0; r < RB; ++r) {
+                            const float diff = Ac[r * AMAX + s_idx] - MU[r * AMAX + s_idx];
+                            acc = fmaf(Rc[r * 8 + 5], diff * diff * inv_var - 1.f, acc);
                         }
                         g_s += acc - a.ent_coef * (float)rows * invB;
                     }
@@ -608,10 +697,11 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                     __syncthreads();
 
                     // ---- dW2 += dH2pre^T H1 ; db2 ; dH1pre = (dH2pre W2) * (1 - H1^2) -> written over H2
-                    outer_tile_4x4(g_w2, DH, H, H1, H, rows, tj2, tk2);
+                    outer_tile_4x4(g_w2, DH, H, H1, H, tj2, tk2);
                     if (s_kind == 1) {
                         float acc = 0.f;
-                        for (int r = 0; r < rows; ++r) acc += DH[r * H + s_idx];
+#pragma unroll 8
+                        for (int r = 0; r < RB; ++r) acc += DH[r * H + s_idx];
                         g_s += acc;
                     }
                     {
@@ -620,7 +710,7 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                         for (int i = 0; i < 4; ++i)
 #pragma unroll
                             for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-                        gemm_tile_4x4(acc, DH, H, W2, H, ty, tx);   // sum_j dH2[r][j] * W2[j][k]  (W2 row-major == "k-major" in j)
+                        gemm_tile_4x4<H>(acc, DH, H, W2, H, ty, tx);   // sum_j dH2[r][j] * W2[j][k]  (W2 row-major == "k-major" in j)
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const float4 h = *reinterpret_cast<const float4*>(H1 + (4 * ty + i) * H + 4 * tx);
@@ -634,38 +724,18 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
 #pragma unroll
                     for (int n = 0; n < NT1; ++n) {
                         const int t = tid + NTH * n;
-                        if (t < n_w1_tiles) outer_tile_4x4(g_w1[n], H2, H, X, DP, rows, t & 15, t >> 4);
+                        if (t < n_w1_tiles) outer_tile_4x4(g_w1[n], H2, H, Xc, DP, t & 15, t >> 4);
                     }
                     if (s_kind == 0) {
                         float acc = 0.f;
-                        for (int r = 0; r < rows; ++r) acc += H2[r * H + s_idx];
+#pragma unroll 8
+                        for (int r = 0; r < RB; ++r) acc += H2[r * H + s_idx];
                         g_s += acc;
                     }
                 }  // chunks
             }      // working
 
-            // ---- loss statistics of this step
-            const size_t so = (size_t)step * ICRL_PPO_STATS_PER_STEP;
-            float kl_step = 0.f;
-            if (role == 0) {
-                const float t_min = block_sum(s_a, scratch), t_cr = block_sum(s_b, scratch), t_clip = block_sum(s_c, scratch),
-                            t_kl = block_sum(s_d, scratch), t_ent = block_sum(s_e, scratch);
-                float pl = -(t_min * invB);
-                pl = pl + nu * (t_cr * invB);
-                pl = pl / (1.f + nu);
-                kl_step = t_kl * invB;
-                if (tid == 0) {
-                    a.stats[so + 0] = pl;
-                    a.stats[so + 1] = t_clip * invB;
-                    a.stats[so + 4] = -(t_ent * invB);
-                    a.stats[so + 5] = kl_step;
-                }
-            } else if (working) {
-                const float t_se = block_sum(s_a, scratch);
-                if (tid == 0) a.stats[so + (role == 1 ? 2 : 3)] = t_se * invB;
-            }
-
-            // ---- global gradient norm: local sum of squares -> DSMEM exchange -> cluster barrier
+            // ---- one merged block reduction: loss partial sums + local sum of squared gradients
             float ss = 0.f;
             if (working) {
 #pragma unroll
@@ -680,7 +750,40 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                 }
                 ss = fmaf(g_s, g_s, ss);
             }
-            ss = block_sum(ss, scratch);
+            float red[6] = {s_a, s_b, s_c, s_d, s_e, ss};
+#pragma unroll
+            for (int i = 0; i < 6; ++i) red[i] = warp_sum(red[i]);
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) scratch[warp * 8 + i] = red[i];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                float t = 0.f;
+#pragma unroll
+                for (int wv = 0; wv < NTH / 32; ++wv) t += scratch[wv * 8 + i];
+                red[i] = t;
+            }
+            ss = red[5];
+            const size_t so = (size_t)step * ICRL_PPO_STATS_PER_STEP;
+            float kl_step = 0.f;
+            if (role == 0) {
+                float pl = -(red[0] * invB);
+                pl = pl + nu * (red[1] * invB);
+                pl = pl / (1.f + nu);
+                kl_step = red[3] * invB;
+                if (tid == 0) {
+                    a.stats[so + 0] = pl;
+                    a.stats[so + 1] = red[2] * invB;
+                    a.stats[so + 4] = -(red[4] * invB);
+                    a.stats[so + 5] = kl_step;
+                }
+            } else if (working) {
+                if (tid == 0) a.stats[so + (role == 1 ? 2 : 3)] = red[0] * invB;
+            }
+
+            // ---- global gradient norm: local sum of squares -> DSMEM exchange -> cluster barrier
             // epoch-level KL early stop is decided by the pi CTA right here (it has this step's KL) and rides along
             float stop_flag = 0.f;
             if (role == 0) {
@@ -711,7 +814,7 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                 ac.one_minus_b1 = (float)(1.0 - a.beta1);
                 ac.b2 = (float)a.beta2;
                 ac.one_minus_b2 = (float)(1.0 - a.beta2);
-                ac.bc2_sqrt = (float)sqrt(1.0 - b2_pow);
+                ac.inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - b2_pow));
                 ac.eps = (float)a.adam_eps;
                 ac.neg_step_size = (float)(-(a.lr / (1.0 - b1_pow)));
 #pragma unroll
@@ -754,9 +857,11 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
             }
             if (stop_rx == 1.f) { early_stop_epoch = epoch; stop_all = true; }
             if (stop_rx == 2.f) { stop_all = true; }
-            __syncthreads();
+            // (the next chunk's leading __syncthreads orders these shared-memory weight updates before their first use)
         }  // minibatches
     }      // epochs
+    cp_async_wait_all();
+    __syncthreads();
 
     // ---- write back parameters and moments
     if (working) {
@@ -844,7 +949,7 @@ __global__ void __launch_bounds__(NTH) policy_forward_kernel(const __grid_consta
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = B1[4 * tx + j];
-        gemm_tile_4x4(acc, X, DP, W1t, DP, ty, tx);
+        gemm_tile_4x4<0>(acc, X, DP, W1t, DP, ty, tx);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
             *reinterpret_cast<float4*>(H1 + (4 * ty + i) * H + 4 * tx) =
@@ -854,7 +959,7 @@ __global__ void __launch_bounds__(NTH) policy_forward_kernel(const __grid_consta
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = B2[4 * tx + j];
-        gemm_tile_4x4(acc, H1, H, W2t, H, ty, tx);
+        gemm_tile_4x4<H>(acc, H1, H, W2t, H, ty, tx);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
             *reinterpret_cast<float4*>(H2 + (4 * ty + i) * H + 4 * tx) =
@@ -989,6 +1094,17 @@ int icrl_ppo_train(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* pa
     a.nu_dev = data->nu_device;
     a.params = params; a.adam_m = adam_m; a.adam_v = adam_v; a.stats = step_stats; a.result = result;
     a.step_before = adam_step_before;
+    {
+        const int total_steps = a.n_epochs * a.steps_per_epoch;
+        void *poff, *advstats;
+        if ((rc = icrl::device_scratch(icrl::SLOT_PPO0, (size_t)a.n_epochs * a.N * sizeof(int), &poff))) return rc;
+        if ((rc = icrl::device_scratch(icrl::SLOT_PPO1, (size_t)total_steps * 4 * sizeof(float), &advstats))) return rc;
+        icrl::ppo_prologue_kernel<<<total_steps, 128, 0, (cudaStream_t)stream>>>(
+            a.perm, (int*)poff, (float*)advstats, a.adv_r, a.adv_c, a.T, a.E, a.N, a.B, a.steps_per_epoch);
+        ICRL_LAUNCH_CHECK();
+        a.poff = (const int*)poff;
+        a.advstats = (const float*)advstats;
+    }
     const int n_tiles = 16 * (a.DP / 4);
     const int nt1 = (n_tiles + icrl::NTH - 1) / icrl::NTH;
     switch (nt1) {
