@@ -16,6 +16,7 @@
 //     shared-memory operand reads (fp32 tolerances of the north star rule out single-pass TF32/BF16 tensor cores).
 // Rollout data stay in the buffer's time-major layout; env-major minibatch indices are translated here.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -25,6 +26,7 @@ constexpr int H = 64;          // padded hidden width (both layers)
 constexpr int RB = 64;         // rows per chunk
 constexpr int NTH = 256;       // threads per CTA
 constexpr int AMAX = 16;       // max action dims / discrete actions
+constexpr int LDH = 68;        // row stride of the activation tiles in the train kernel (bank-conflict-free float4 rows)
 constexpr int WA_LD = 68;      // leading dim of the action head weight in smem (bank-conflict-free float4 rows)
 constexpr float LOG_SQRT_2PI = 0.91893853320467274178f;
 constexpr float HALF_LOG_2PI_PLUS_HALF = 1.4189385332046727418f;
@@ -40,11 +42,13 @@ struct PpoArgs {
     int off_logstd, off_w1[3], off_b1[3], off_w2[3], off_b2[3], off_hw[3], off_hb[3];
     const float *obs, *act, *old_logp, *old_vr, *adv_r, *ret_r, *old_vc, *adv_c, *ret_c;
     const int* perm;
-    const int* poff;          // perm translated to time-major element offsets (prologue kernel)
-    const float* advstats;    // [steps][4]: mean(adv_r), std(adv_r) (unbiased), mean(adv_c) per minibatch
+    const float *xs, *as, *ss; // minibatch-ordered streams built by the prologue: obs [P][DP], actions [P][AP], scalars [P][8]
+    int AP;                    // padded action width of the stream (multiple of 4)
+    const float* advstats;    // [steps][8]: mean(adv_r), std(adv_r) (unbiased), mean(adv_c), 1/sqrt(1-b2^t), -lr/(1-b1^t)
     const float* nu_dev;
     float *params, *adam_m, *adam_v, *stats;
     int* result;
+    unsigned long long* timing;   // optional [3 roles][16 phases] cycle accumulators (profiling aid)
 };
 
 // ---------------------------------------------------------------- cluster primitives (raw PTX)
@@ -69,6 +73,12 @@ __device__ __forceinline__ void st_remote_f32(float* local_ptr, uint32_t rank, f
 
 __device__ __forceinline__ void cp_async_4(void* dst_smem, const void* src_gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
@@ -97,7 +107,7 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
 
 // ---------------------------------------------------------------- shared memory carve-up (float offsets)
 struct PpoSmem {
-    int w1t, w2t, w2, b1, b2, hw, hb, logstd, x, h1, h2, dh, rowf, dmean, act, mu, rowoff, scratch, xch, total_bytes;
+    int w1t, w2t, w2, b1, b2, hw, hb, logstd, sig, x, h1, h2, dh, rowf, dmean, act, mu, rowoff, scratch, xch, total_bytes;
 };
 __host__ __device__ inline PpoSmem ppo_smem_layout(int DP) {
     PpoSmem s;
@@ -110,15 +120,16 @@ __host__ __device__ inline PpoSmem ppo_smem_layout(int DP) {
     s.hw = o; o += AMAX * WA_LD;
     s.hb = o; o += AMAX;
     s.logstd = o; o += AMAX;
+    s.sig = o; o += 2 * AMAX;        // per action dim: 1/sigma^2, log(sigma) -- refreshed by the thread that updates log_std
     s.x = o; o += 2 * RB * DP;      // double buffered (cp.async prefetch of the next chunk)
-    s.h1 = o; o += RB * H;
-    s.h2 = o; o += RB * H;
-    s.dh = o; o += RB * H;
+    s.h1 = o; o += RB * LDH;
+    s.h2 = o; o += RB * LDH;
+    s.dh = o; o += RB * LDH;
     s.rowf = o; o += 2 * RB * 8;      // per-row scalars: 0 old_logp, 1 adv_r~, 2 adv_c~, 3 target return, 4 old value, 5 g/dV
     s.dmean = o; o += RB * AMAX;
     s.act = o; o += 2 * RB * AMAX;
     s.mu = o; o += RB * AMAX;        // action-head outputs (means / logits)
-    s.rowoff = o; o += 3 * RB;       // int: 3-deep ring of chunk row offsets t*E+e (-1 = padding)
+    s.rowoff = o; o += 4;            // two 8-byte mbarriers (one per chunk buffer)
     s.scratch = o; o += 64;         // 32 floats / 16 doubles of reduction scratch (8-byte aligned: o is even)
     s.xch = o; o += 2 * 4 * 2;      // [parity][rank][{sumsq, stop}]
     s.total_bytes = o * 4;
@@ -127,7 +138,9 @@ __host__ __device__ inline PpoSmem ppo_smem_layout(int DP) {
 
 // 64x64 += A[64 x K] * Bt[K x 64]  (A row-major lda, Bt k-major ld 64); thread tile rows 4ty.., cols 4tx..
 // KC > 0: compile-time K (fully unrolled so operand loads run ahead of the FMAs); KC == 0: runtime K.
-template <int KC>
+// SWZ: Bt's float4 column slots are XOR-swizzled with (k >> 2) & 15 (the W2t copy: lets the Adam phase write the
+// transposed tile with conflict-free 128-bit stores while these row reads stay conflict-free).
+template <int KC, bool SWZ = false>
 __device__ __forceinline__ void gemm_tile_4x4(float (&acc)[4][4], const float* __restrict__ A, int lda,
                                               const float* __restrict__ Bt, int K, int ty, int tx) {
     const float* a0 = A + (4 * ty) * lda;
@@ -139,7 +152,9 @@ __device__ __forceinline__ void gemm_tile_4x4(float (&acc)[4][4], const float* _
 #pragma unroll
         for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + i * lda + k);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) w[kk] = *reinterpret_cast<const float4*>(b0 + (k + kk) * H);
+        for (int kk = 0; kk < 4; ++kk)
+            w[kk] = SWZ ? *reinterpret_cast<const float4*>(Bt + (k + kk) * H + 4 * (tx ^ ((k >> 2) & 15)))
+                        : *reinterpret_cast<const float4*>(b0 + (k + kk) * H);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
@@ -174,6 +189,16 @@ __device__ __forceinline__ void outer_tile_4x4(float (&acc)[4][4], const float* 
     }
 }
 
+// (unused: measured no gain, kept for reference) tanh(x) = 1 - 2 / (1 + e^{2x}) on the SFU (ex2.approx + rcp.approx): ~7 instructions instead of tanhf's ~30, absolute
+// error <= 2e-7 (about 2 ulp of 1.0), saturates correctly to +-1 for large |x|.
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float e = __expf(2.f * x);
+    return 1.f - __fdividef(2.f, 1.f + e);
+}
+
+// physical column of element (k, j) in the swizzled transposed copy W2t[k][.]
+__device__ __forceinline__ int w2t_col(int k, int j) { return (((j >> 2) ^ ((k >> 2) & 15)) << 2) | (j & 3); }
+
 // one Adam update in torch's single-tensor form (torch/optim/adam.py); returns the new parameter
 struct AdamConsts {
     float one_minus_b1, b2, one_minus_b2, inv_bc2_sqrt, eps, neg_step_size;
@@ -187,15 +212,49 @@ __device__ __forceinline__ float adam_update(float p, float g, float& m, float& 
     return fmaf(c.neg_step_size, __fdividef(m, denom), p);
 }
 
-// ---------------------------------------------------------------- prologue: one CTA per optimiser step
-// (i) numpy's env-major minibatch indices (row = e*T + t, buffers.py:52-65) -> time-major element offsets t*E + e,
-// (ii) the minibatch statistics of ppo_lag.py:218-222: mean and unbiased std of the reward advantages, mean of the cost
-// advantages (float64 accumulation like ATen's CPU reductions).  They depend only on data, never on parameters, so all
-// 1 600 of them are computed in parallel here instead of inside the dependent step chain.
-__global__ void __launch_bounds__(128) ppo_prologue_kernel(const int* __restrict__ perm, int* __restrict__ poff,
-                                                           float* __restrict__ advstats, const float* __restrict__ adv_r,
-                                                           const float* __restrict__ adv_c, int T, int E, int N, int B,
-                                                           int spe) {
+// ---------------------------------------------------------------- prologue kernels (massively parallel, HBM-bound)
+// The minibatch schedule is known before the first optimiser step (numpy's permutations come from the host), so the
+// random-access gather is taken OUT of the dependent step chain: one pass builds minibatch-ordered streams
+//     xs[p][DP] obs (zero padded), as[p][AP] actions, ss[p][8] = {old_logp, adv_r, adv_c, ret_r, old_vr, ret_c, old_vc, -}
+// for p = epoch*N + position, translating numpy's env-major index (row = e*T + t, buffers.py:52-65) to the buffer's
+// time-major storage on the fly.  The persistent kernel then fetches each 64-row chunk with TMA bulk copies.
+__global__ void __launch_bounds__(256) ppo_gather_kernel(const __grid_constant__ PpoArgs a, float* __restrict__ xs,
+                                                         float* __restrict__ as, float* __restrict__ ss,
+                                                         long long n_rows, long long n_alloc) {
+    const int lane = threadIdx.x & 31;
+    const int aw = a.is_discrete ? 1 : a.A;
+    for (long long p = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); p < n_alloc; p += (long long)gridDim.x * 8) {
+        int o = -1;
+        if (p < n_rows) {
+            const int row = a.perm[p], t = row % a.T, e = row / a.T;
+            o = t * a.E + e;
+        }
+        for (int k = lane; k < a.DP; k += 32) xs[p * a.DP + k] = (o >= 0 && k < a.D) ? a.obs[(size_t)o * a.D + k] : 0.f;
+        if (lane < a.AP) as[p * a.AP + lane] = (o >= 0 && lane < aw) ? a.act[(size_t)o * aw + lane] : 0.f;
+        if (lane < 8) {
+            float v = 0.f;
+            if (o >= 0) {
+                switch (lane) {
+                    case 0: v = a.old_logp[o]; break;
+                    case 1: v = a.adv_r[o]; break;
+                    case 2: v = a.adv_c[o]; break;
+                    case 3: v = a.ret_r[o]; break;
+                    case 4: v = a.old_vr[o]; break;
+                    case 5: v = a.ret_c[o]; break;
+                    case 6: v = a.old_vc[o]; break;
+                }
+            }
+            ss[p * 8 + lane] = v;
+        }
+    }
+}
+
+// One CTA per optimiser step: the minibatch statistics of ppo_lag.py:218-222 (mean and unbiased std of the reward
+// advantages, mean of the cost advantages; float64 accumulation like ATen's CPU reductions) and that step's Adam bias
+// corrections.  They depend only on data and the step number, never on parameters.
+__global__ void __launch_bounds__(128) ppo_stats_kernel(const float* __restrict__ ss, float* __restrict__ advstats, int N,
+                                                        int B, int spe, double beta1, double beta2, double lr,
+                                                        long long step_before) {
     __shared__ double red[2][4];
     const int step = blockIdx.x, epoch = step / spe, mb = step - epoch * spe;
     const int Bn = min(B, N - mb * B);
@@ -203,10 +262,8 @@ __global__ void __launch_bounds__(128) ppo_prologue_kernel(const int* __restrict
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double sr = 0.0, sc = 0.0;
     for (int i = tid; i < Bn; i += blockDim.x) {
-        const int row = perm[base + i], t = row % T, e = row / T, o = t * E + e;
-        poff[base + i] = o;
-        sr += (double)adv_r[o];
-        sc += (double)adv_c[o];
+        sr += (double)ss[(base + i) * 8 + 1];
+        sc += (double)ss[(base + i) * 8 + 2];
     }
     sr = warp_sum(sr); sc = warp_sum(sc);
     if (lane == 0) { red[0][warp] = sr; red[1][warp] = sc; }
@@ -216,8 +273,7 @@ __global__ void __launch_bounds__(128) ppo_prologue_kernel(const int* __restrict
     __syncthreads();
     double ssq = 0.0;
     for (int i = tid; i < Bn; i += blockDim.x) {
-        const int row = perm[base + i], t = row % T, e = row / T;
-        const double dv = (double)adv_r[t * E + e] - mr;
+        const double dv = (double)ss[(base + i) * 8 + 1] - mr;
         ssq += dv * dv;
     }
     ssq = warp_sum(ssq);
@@ -225,10 +281,13 @@ __global__ void __launch_bounds__(128) ppo_prologue_kernel(const int* __restrict
     __syncthreads();
     if (tid == 0) {
         const double tot = red[0][0] + red[0][1] + red[0][2] + red[0][3];
-        advstats[step * 4 + 0] = (float)mr;
-        advstats[step * 4 + 1] = (float)sqrt(tot / (double)(Bn - 1));
-        advstats[step * 4 + 2] = (float)mc;
-        advstats[step * 4 + 3] = 0.f;
+        advstats[step * 8 + 0] = (float)mr;
+        advstats[step * 8 + 1] = (float)sqrt(tot / (double)(Bn - 1));
+        advstats[step * 8 + 2] = (float)mc;
+        // Adam bias corrections of optimiser step t (torch/optim/adam.py: 1 - beta ** step, python float64 pow)
+        const double t = (double)(step_before + step + 1);
+        advstats[step * 8 + 3] = (float)(1.0 / sqrt(1.0 - pow(beta2, t)));
+        advstats[step * 8 + 4] = (float)(-(lr / (1.0 - pow(beta1, t))));
     }
 }
 
@@ -248,10 +307,10 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
 
     float* W1t = sm + L.w1t; float* W2t = sm + L.w2t; float* W2 = sm + L.w2;
     float* B1 = sm + L.b1; float* B2 = sm + L.b2; float* HW = sm + L.hw; float* HB = sm + L.hb;
-    float* LOGSTD = sm + L.logstd;
+    float* LOGSTD = sm + L.logstd; float* SIG = sm + L.sig;
     float* X = sm + L.x; float* H1 = sm + L.h1; float* H2 = sm + L.h2; float* DH = sm + L.dh;
     float* ROWF = sm + L.rowf; float* DMEAN = sm + L.dmean; float* ACT = sm + L.act; float* MU = sm + L.mu;
-    int* IDX = reinterpret_cast<int*>(sm + L.rowoff);
+    uint64_t* BAR = reinterpret_cast<uint64_t*>(sm + L.rowoff);
     float* scratch = sm + L.scratch;
     float* XCH = sm + L.xch;
 
@@ -288,9 +347,6 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
     if (tid < H) { B1[tid] = 0.f; B2[tid] = 0.f; }
     if (tid < AMAX) { HB[tid] = 0.f; LOGSTD[tid] = 0.f; }
     if (tid < 16) XCH[tid] = 0.f;
-    for (int i = tid; i < 2 * RB * DP; i += NTH) X[i] = 0.f;     // padding columns k in [D, DP) stay zero forever
-    for (int i = tid; i < 2 * RB * 8; i += NTH) ROWF[i] = 0.f;
-    for (int i = tid; i < 2 * RB * AMAX; i += NTH) ACT[i] = 0.f;
     __syncthreads();
     if (working) {
 #pragma unroll
@@ -300,7 +356,7 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                 const int j = 4 * tj2 + jj, k = 4 * tk2 + kk, f = flat_w2(j, k);
                 m_w2[jj][kk] = f >= 0 ? a.adam_m[f] : 0.f;
                 v_w2[jj][kk] = f >= 0 ? a.adam_v[f] : 0.f;
-                if (f >= 0) { const float w = a.params[f]; W2[j * H + k] = w; W2t[k * H + j] = w; }
+                if (f >= 0) { const float w = a.params[f]; W2[j * H + k] = w; W2t[k * H + w2t_col(k, j)] = w; }
             }
 #pragma unroll
         for (int n = 0; n < NT1; ++n) {
@@ -334,93 +390,66 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
         }
     }
     __syncthreads();
+    if (tid < AMAX) {
+        const float sigma = expf(LOGSTD[tid]);
+        SIG[tid] = 1.f / (sigma * sigma);
+        SIG[AMAX + tid] = logf(sigma);
+    }
+    __syncthreads();
     cluster_sync_all();   // every CTA has zeroed its exchange slots before any peer writes into them
 
-    // bias-correction powers, advanced multiplicatively each step (double)
-    double b1_pow = pow(a.beta1, (double)a.step_before), b2_pow = pow(a.beta2, (double)a.step_before);
     const int ty = tid >> 4, tx = tid & 15;     // forward tile: rows 4ty.., cols 4tx..
     const int hr = tid >> 2, hq = tid & 3;      // head mapping: row hr, quarter hq
     const int warp = tid >> 5, lane = tid & 31;
     const int aw = a.is_discrete ? 1 : a.A;
+    // widest cp.async the obs rows allow (row stride D floats, 16-byte aligned base)
+    const int xvec = ((reinterpret_cast<uintptr_t>(a.obs) & 15) == 0) ? ((D % 4 == 0) ? 4 : (D % 2 == 0) ? 2 : 1) : 1;
 
-    // ---- chunk pipeline: the (epoch, minibatch, 64-row chunk) sequence is known up front (the prologue kernel turned
-    // numpy's permutations into time-major element offsets), so chunk q+1's rows are gathered with cp.async while chunk q
-    // is being computed, and chunk q+2's offsets are fetched one stage earlier still.  No global latency is exposed.
+    // ---- chunk pipeline: chunk q+1 of the minibatch-ordered streams is fetched by TMA bulk copies (one elected thread,
+    // completion on an mbarrier) while chunk q is being computed.  No global latency is exposed to the step chain.
     struct Cursor { int epoch, mb, c0; };
     auto cur_valid = [&](const Cursor& c) { return c.epoch < a.n_epochs; };
     auto cur_bn = [&](const Cursor& c) { return min(a.B, a.N - c.mb * a.B); };
-    auto cur_rows = [&](const Cursor& c) { return min(RB, cur_bn(c) - c.c0); };
     auto cur_next = [&](Cursor c) {
         c.c0 += RB;
         if (c.c0 >= cur_bn(c)) { c.c0 = 0; if (++c.mb >= a.steps_per_epoch) { c.mb = 0; ++c.epoch; } }
         return c;
     };
-    auto prefetch_idx = [&](const Cursor& c, int slot) {          // offsets of the chunk's rows -> IDX[slot] (-1 = padding)
-        if (tid < RB) {
-            int* dst = IDX + slot * RB + tid;
-            if (cur_valid(c) && tid < cur_rows(c))
-                cp_async_4(dst, a.poff + (size_t)c.epoch * a.N + (size_t)c.mb * a.B + c.c0 + tid);
-            else
-                *dst = -1;
-        }
-    };
-    auto prefetch_data = [&](int slot, int buf) {                 // gather the rows named by IDX[slot] into buffer `buf`
-        const int* offs = IDX + slot * RB;
-        float* Xb = X + buf * RB * DP;
-        for (int r = warp; r < RB; r += NTH / 32) {
-            const int o = offs[r];
-            if (o >= 0) {
-                const float* src = a.obs + (size_t)o * D;
-                for (int k = lane; k < D; k += 32) cp_async_4(Xb + r * DP + k, src + k);
-            } else {
-                for (int k = lane; k < D; k += 32) Xb[r * DP + k] = 0.f;
-            }
-        }
-        float* Rb = ROWF + buf * RB * 8;
-        if (tid < RB) {
-            const int o = offs[tid];
-            if (o >= 0) {
-                if (role == 0) {
-                    cp_async_4(Rb + tid * 8 + 0, a.old_logp + o);
-                    cp_async_4(Rb + tid * 8 + 1, a.adv_r + o);
-                    cp_async_4(Rb + tid * 8 + 2, a.adv_c + o);
-                } else if (role == 1) {
-                    cp_async_4(Rb + tid * 8 + 3, a.ret_r + o);
-                    cp_async_4(Rb + tid * 8 + 4, a.old_vr + o);
-                } else {
-                    cp_async_4(Rb + tid * 8 + 3, a.ret_c + o);
-                    cp_async_4(Rb + tid * 8 + 4, a.old_vc + o);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 5; ++i) Rb[tid * 8 + i] = 0.f;
-            }
-        }
-        if (role == 0) {
-            float* Ab = ACT + buf * RB * AMAX;
-            const int r = tid >> 2, o = offs[r];
-            for (int d = tid & 3; d < aw; d += 4) {
-                if (o >= 0) cp_async_4(Ab + r * AMAX + d, a.act + (size_t)o * aw + d);
-                else Ab[r * AMAX + d] = 0.f;
-            }
-        }
+    const int AP = a.AP;
+    auto fetch_chunk = [&](const Cursor& c, int buf) {   // called by thread 0 only
+        const size_t p = (size_t)c.epoch * a.N + (size_t)c.mb * a.B + c.c0;   // streams carry RB rows of tail padding
+        const uint32_t xb = RB * DP * 4, sb = RB * 8 * 4, ab = (role == 0) ? RB * AP * 4 : 0;
+        fence_proxy_async();   // earlier generic-proxy accesses to this buffer are ordered before the async-proxy writes
+        mbar_expect_tx(&BAR[buf], xb + sb + ab);
+        bulk_g2s(X + buf * RB * DP, a.xs + p * DP, xb, &BAR[buf]);
+        bulk_g2s(ROWF + buf * RB * 8, a.ss + p * 8, sb, &BAR[buf]);
+        if (role == 0) bulk_g2s(ACT + buf * RB * AMAX, a.as + p * AP, ab, &BAR[buf]);
     };
 
     Cursor cur = {0, 0, 0};
-    int q = 0;                                   // running chunk counter (buffer / slot parity)
-    if (working) {
-        prefetch_idx(cur, 0);
-        prefetch_idx(cur_next(cur), 1);
-        cp_async_commit();
-        cp_async_wait_all();
-        __syncthreads();
-        prefetch_data(0, 0);
-        cp_async_commit();
+    int q = 0;                                   // running chunk counter (buffer parity / mbarrier phase)
+    if (tid == 0) {
+        mbar_init(&BAR[0], 1);
+        mbar_init(&BAR[1], 1);
+        fence_mbar_init();
     }
+    __syncthreads();
+    if (working && tid == 0) fetch_chunk(cur, 0);
 
     int step = 0, early_stop_epoch = a.n_epochs;
     double epoch_kl_sum = 0.0;
     bool stop_all = false;
+    const bool timed = (a.timing != nullptr) && tid == 0 && working;
+    long long tmark = clock64();
+    unsigned long long tacc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) tacc[i] = 0;
+#define ICRL_MARK(i)                                   \
+    if (timed) {                                       \
+        const long long now__ = clock64();             \
+        tacc[i] += (unsigned long long)(now__ - tmark); \
+        tmark = now__;                                 \
+    }
 
     for (int epoch = 0; epoch < a.n_epochs && !stop_all; ++epoch) {
         epoch_kl_sum = 0.0;
@@ -445,8 +474,9 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
             // loss partial sums (thread-local, one merged block reduction at the end of the step)
             float s_a = 0.f, s_b = 0.f, s_c = 0.f, s_d = 0.f, s_e = 0.f;
             // minibatch statistics of the advantages (ppo_lag.py:218-222) from the prologue kernel's table
-            const float adv_mean_r = a.advstats[step * 4 + 0], adv_std_r = a.advstats[step * 4 + 1],
-                        adv_mean_c = a.advstats[step * 4 + 2];
+            const float adv_mean_r = a.advstats[step * 8 + 0], adv_std_r = a.advstats[step * 8 + 1],
+                        adv_mean_c = a.advstats[step * 8 + 2];
+            const float adam_inv_bc2_sqrt = a.advstats[step * 8 + 3], adam_neg_step = a.advstats[step * 8 + 4];
 
             if (working) {
                 for (int c0 = 0; c0 < Bn; c0 += RB, ++q) {
@@ -454,17 +484,16 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                     const int buf = q & 1;
                     const float* Xc = X + buf * RB * DP;
                     float* Rc = ROWF + buf * RB * 8;
-                    const float* Ac = ACT + buf * RB * AMAX;
-                    cp_async_wait_all();
-                    __syncthreads();          // chunk q landed (and everybody is done with chunk q-1's buffers)
+                    const float* Ac = ACT + buf * RB * AMAX;   // rows at stride AP (as the stream stores them)
+                    mbar_wait(&BAR[buf], (uint32_t)((q >> 1) & 1));
+                    __syncthreads();          // chunk q landed, and everybody is done with chunk q-1's buffers
+                    ICRL_MARK(0)
                     {
                         const Cursor nxt = cur_next(cur);
-                        if (cur_valid(nxt)) prefetch_data((q + 1) % 3, buf ^ 1);
-                        prefetch_idx(cur_next(nxt), (q + 2) % 3);
-                        cp_async_commit();
+                        if (tid == 0 && cur_valid(nxt)) fetch_chunk(nxt, buf ^ 1);
                         cur = nxt;
                     }
-
+                    ICRL_MARK(1)
                     // ---- forward layer 1: H1 = tanh(X W1^T + b1)
                     {
                         float acc[4][4];
@@ -475,10 +504,11 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                         gemm_tile_4x4<0>(acc, Xc, DP, W1t, DP, ty, tx);
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            *reinterpret_cast<float4*>(H1 + (4 * ty + i) * H + 4 * tx) =
+                            *reinterpret_cast<float4*>(H1 + (4 * ty + i) * LDH + 4 * tx) =
                                 make_float4(tanhf(acc[i][0]), tanhf(acc[i][1]), tanhf(acc[i][2]), tanhf(acc[i][3]));
                     }
                     __syncthreads();
+                    ICRL_MARK(2)
                     // ---- forward layer 2: H2 = tanh(H1 W2^T + b2)
                     {
                         float acc[4][4];
@@ -486,14 +516,15 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                         for (int i = 0; i < 4; ++i)
 #pragma unroll
                             for (int j = 0; j < 4; ++j) acc[i][j] = B2[4 * tx + j];
-                        gemm_tile_4x4<H>(acc, H1, H, W2t, H, ty, tx);
+                        gemm_tile_4x4<H, true>(acc, H1, LDH, W2t, H, ty, tx);
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            *reinterpret_cast<float4*>(H2 + (4 * ty + i) * H + 4 * tx) =
+                            *reinterpret_cast<float4*>(H2 + (4 * ty + i) * LDH + 4 * tx) =
                                 make_float4(tanhf(acc[i][0]), tanhf(acc[i][1]), tanhf(acc[i][2]), tanhf(acc[i][3]));
                     }
                     __syncthreads();
 
+                    ICRL_MARK(3)
                     // ---- heads + losses + d(loss)/d(head output).  4 threads per row (hr, hq).
                     if (role == 0) {
                         // action head: outputs d = hq, hq+4, hq+8, hq+12
@@ -503,15 +534,16 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                             const int d = hq + 4 * u;
                             float acc = 0.f;
                             if (d < a.A) {
-                                acc = HB[d];
-                                const float4* hrow = reinterpret_cast<const float4*>(H2 + hr * H);
+                                const float4* hrow = reinterpret_cast<const float4*>(H2 + hr * LDH);
                                 const float4* wrow = reinterpret_cast<const float4*>(HW + d * WA_LD);
+                                float p0 = HB[d], p1 = 0.f, p2 = 0.f, p3 = 0.f;     // 4 independent chains
 #pragma unroll
                                 for (int k = 0; k < H / 4; ++k) {
                                     const float4 h = hrow[k], w = wrow[k];
-                                    acc = fmaf(h.x, w.x, acc); acc = fmaf(h.y, w.y, acc);
-                                    acc = fmaf(h.z, w.z, acc); acc = fmaf(h.w, w.w, acc);
+                                    p0 = fmaf(h.x, w.x, p0); p1 = fmaf(h.y, w.y, p1);
+                                    p2 = fmaf(h.z, w.z, p2); p3 = fmaf(h.w, w.w, p3);
                                 }
+                                acc = (p0 + p1) + (p2 + p3);
                             }
                             out[u] = acc;
                             MU[hr * AMAX + d] = acc;
@@ -526,12 +558,11 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                             for (int u = 0; u < 4; ++u) {
                                 const int d = hq + 4 * u;
                                 if (d < a.A) {
-                                    const float sigma = expf(LOGSTD[d]);
-                                    const float var = sigma * sigma, log_scale = logf(sigma);
-                                    const float diff = Ac[hr * AMAX + d] - out[u];
-                                    lp += -(diff * diff) / (2.f * var) - log_scale - LOG_SQRT_2PI;
+                                    const float inv_var = SIG[d], log_scale = SIG[AMAX + d];
+                                    const float diff = Ac[hr * AP + d] - out[u];
+                                    lp += -(diff * diff) * (0.5f * inv_var) - log_scale - LOG_SQRT_2PI;
                                     en += HALF_LOG_2PI_PLUS_HALF + log_scale;
-                                    dcoef[u] = diff / var;
+                                    dcoef[u] = diff * inv_var;
                                 }
                             }
                             lp += __shfl_xor_sync(0xffffffffu, lp, 1); lp += __shfl_xor_sync(0xffffffffu, lp, 2);
@@ -548,7 +579,7 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                             for (int u = 0; u < 4; ++u) if (hq + 4 * u < a.A) se += expf(out[u] - mx);
                             se += __shfl_xor_sync(0xffffffffu, se, 1); se += __shfl_xor_sync(0xffffffffu, se, 2);
                             const float lse = mx + logf(se);
-                            const int ai = (int)Ac[hr * AMAX + 0];
+                            const int ai = (int)Ac[hr * AP + 0];
                             float lp = 0.f, en = 0.f, pr[4], lg[4];
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
@@ -604,11 +635,11 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                             const int d = hq + 4 * u;
                             if (d < AMAX) DMEAN[hr * AMAX + d] = (d < a.A) ? (g * dcoef[u] + ge * dent[u]) : 0.f;
                         }
-                        if (hq == 0) Rc[hr * 8 + 5] = g;
+                        if (hq == 0) Rc[hr * 8 + 7] = g;
                     } else {
                         // value head: partial dot over k in [16hq, 16hq+16)
                         float acc = 0.f;
-                        const float4* hrow = reinterpret_cast<const float4*>(H2 + hr * H + 16 * hq);
+                        const float4* hrow = reinterpret_cast<const float4*>(H2 + hr * LDH + 16 * hq);
                         const float4* wrow = reinterpret_cast<const float4*>(HW + 16 * hq);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
@@ -619,7 +650,7 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
                         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
                         const float V = acc + HB[0];
-                        const float target = Rc[hr * 8 + 3], oldv = Rc[hr * 8 + 4];
+                        const float target = Rc[hr * 8 + (role == 1 ? 3 : 5)], oldv = Rc[hr * 8 + (role == 1 ? 4 : 6)];
                         const bool clipvf = (role == 1) ? a.has_clip_vf_r : a.has_clip_vf_c;
                         const float cr = (role == 1) ? a.clip_vf_r : a.clip_vf_c;
                         float Vp = V, pass = 1.f;
@@ -639,13 +670,14 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                     }
                     __syncthreads();
 
+                    ICRL_MARK(4)
                     // ---- head weight / bias / log_std gradients (rows beyond `rows` carry zero dmean: loops run over RB)
                     if (hd < AOUT) {
                         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
 #pragma unroll 8
                         for (int r = 0; r < RB; ++r) {
                             const float dm = DMEAN[r * AMAX + hd];
-                            const float4 h = *reinterpret_cast<const float4*>(H2 + r * H + 4 * hk4);
+                            const float4 h = *reinterpret_cast<const float4*>(H2 + r * LDH + 4 * hk4);
                             acc0 = fmaf(dm, h.x, acc0); acc1 = fmaf(dm, h.y, acc1);
                             acc2 = fmaf(dm, h.z, acc2); acc3 = fmaf(dm, h.w, acc3);
                         }
@@ -658,13 +690,12 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                         g_s += acc;
                     } else if (s_kind == 3) {
                         // d logp / d log_std_d = diff^2/var - 1 ; entropy: d(-mean H)/d log_std = -1
-                        const float sigma = expf(LOGSTD[s_idx]);
-                        const float inv_var = 1.f / (sigma * sigma);
+                        const float inv_var = SIG[s_idx];
                         float acc = 0.f;
 #pragma unroll 8
                         for (int r = 0; r < RB; ++r) {
-                            const float diff = Ac[r * AMAX + s_idx] - MU[r * AMAX + s_idx];
-                            acc = fmaf(Rc[r * 8 + 5], diff * diff * inv_var - 1.f, acc);
+                            const float diff = Ac[r * AP + s_idx] - MU[r * AMAX + s_idx];
+                            acc = fmaf(Rc[r * 8 + 7], diff * diff * inv_var - 1.f, acc);
                         }
                         g_s += acc - a.ent_coef * (float)rows * invB;
                     }
@@ -685,8 +716,8 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                                 dloc[4 * k + 3] = fmaf(dm, w.w, dloc[4 * k + 3]);
                             }
                         }
-                        const float4* hrow = reinterpret_cast<const float4*>(H2 + hr * H + 16 * hq);
-                        float4* drow = reinterpret_cast<float4*>(DH + hr * H + 16 * hq);
+                        const float4* hrow = reinterpret_cast<const float4*>(H2 + hr * LDH + 16 * hq);
+                        float4* drow = reinterpret_cast<float4*>(DH + hr * LDH + 16 * hq);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const float4 h = hrow[k];
@@ -696,12 +727,13 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                     }
                     __syncthreads();
 
+                    ICRL_MARK(5)
                     // ---- dW2 += dH2pre^T H1 ; db2 ; dH1pre = (dH2pre W2) * (1 - H1^2) -> written over H2
-                    outer_tile_4x4(g_w2, DH, H, H1, H, tj2, tk2);
+                    outer_tile_4x4(g_w2, DH, LDH, H1, LDH, tj2, tk2);
                     if (s_kind == 1) {
                         float acc = 0.f;
 #pragma unroll 8
-                        for (int r = 0; r < RB; ++r) acc += DH[r * H + s_idx];
+                        for (int r = 0; r < RB; ++r) acc += DH[r * LDH + s_idx];
                         g_s += acc;
                     }
                     {
@@ -710,28 +742,30 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                         for (int i = 0; i < 4; ++i)
 #pragma unroll
                             for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-                        gemm_tile_4x4<H>(acc, DH, H, W2, H, ty, tx);   // sum_j dH2[r][j] * W2[j][k]  (W2 row-major == "k-major" in j)
+                        gemm_tile_4x4<H>(acc, DH, LDH, W2, H, ty, tx);   // sum_j dH2[r][j] * W2[j][k]  (W2 row-major == "k-major" in j)
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const float4 h = *reinterpret_cast<const float4*>(H1 + (4 * ty + i) * H + 4 * tx);
-                            *reinterpret_cast<float4*>(H2 + (4 * ty + i) * H + 4 * tx) =
+                            const float4 h = *reinterpret_cast<const float4*>(H1 + (4 * ty + i) * LDH + 4 * tx);
+                            *reinterpret_cast<float4*>(H2 + (4 * ty + i) * LDH + 4 * tx) =
                                 make_float4(acc[i][0] * (1.f - h.x * h.x), acc[i][1] * (1.f - h.y * h.y),
                                             acc[i][2] * (1.f - h.z * h.z), acc[i][3] * (1.f - h.w * h.w));
                         }
                     }
                     __syncthreads();
+                    ICRL_MARK(6)
                     // ---- dW1 += dH1pre^T X ; db1
 #pragma unroll
                     for (int n = 0; n < NT1; ++n) {
                         const int t = tid + NTH * n;
-                        if (t < n_w1_tiles) outer_tile_4x4(g_w1[n], H2, H, Xc, DP, t & 15, t >> 4);
+                        if (t < n_w1_tiles) outer_tile_4x4(g_w1[n], H2, LDH, Xc, DP, t & 15, t >> 4);
                     }
                     if (s_kind == 0) {
                         float acc = 0.f;
 #pragma unroll 8
-                        for (int r = 0; r < RB; ++r) acc += H2[r * H + s_idx];
+                        for (int r = 0; r < RB; ++r) acc += H2[r * LDH + s_idx];
                         g_s += acc;
                     }
+                    ICRL_MARK(7)
                 }  // chunks
             }      // working
 
@@ -783,6 +817,7 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                 if (tid == 0) a.stats[so + (role == 1 ? 2 : 3)] = red[0] * invB;
             }
 
+            ICRL_MARK(8)
             // ---- global gradient norm: local sum of squares -> DSMEM exchange -> cluster barrier
             // epoch-level KL early stop is decided by the pi CTA right here (it has this step's KL) and rides along
             float stop_flag = 0.f;
@@ -798,6 +833,7 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                 st_remote_f32(XCH + (parity * 4 + role) * 2 + 1, (uint32_t)tid, stop_flag);
             }
             cluster_sync_all();
+            ICRL_MARK(9)
             const float total_ss = XCH[(parity * 4 + 0) * 2] + XCH[(parity * 4 + 1) * 2] + XCH[(parity * 4 + 2) * 2];
             const float stop_rx = XCH[(parity * 4 + 0) * 2 + 1];
             const float total_norm = sqrtf(total_ss);
@@ -809,59 +845,78 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
 
             // ---- Adam (each thread updates the parameters it owns; smem copies refreshed in place)
             if (working) {
-                b1_pow *= a.beta1; b2_pow *= a.beta2;
                 AdamConsts ac;
                 ac.one_minus_b1 = (float)(1.0 - a.beta1);
                 ac.b2 = (float)a.beta2;
                 ac.one_minus_b2 = (float)(1.0 - a.beta2);
-                ac.inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - b2_pow));
+                ac.inv_bc2_sqrt = adam_inv_bc2_sqrt;
                 ac.eps = (float)a.adam_eps;
-                ac.neg_step_size = (float)(-(a.lr / (1.0 - b1_pow)));
+                ac.neg_step_size = adam_neg_step;
+                {
+                    // W2 tile (rows 4tj2.., cols 4tk2..): 128-bit reads/writes of the row-major copy, 128-bit swizzled
+                    // writes of the transposed copy.  Padding entries (j >= h1 or k >= h0) keep g = m = v = 0 and stay 0.
+                    float pw[4][4];
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const int j = 4 * tj2 + jj, k = 4 * tk2 + kk;
-                        if (j < a.h1 && k < a.h0) {
-                            const float p = adam_update(W2[j * H + k], g_w2[jj][kk] * clip_coef, m_w2[jj][kk], v_w2[jj][kk], ac);
-                            W2[j * H + k] = p; W2t[k * H + j] = p;
-                        }
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(W2 + (4 * tj2 + jj) * H + 4 * tk2);
+                        pw[jj][0] = adam_update(w4.x, g_w2[jj][0] * clip_coef, m_w2[jj][0], v_w2[jj][0], ac);
+                        pw[jj][1] = adam_update(w4.y, g_w2[jj][1] * clip_coef, m_w2[jj][1], v_w2[jj][1], ac);
+                        pw[jj][2] = adam_update(w4.z, g_w2[jj][2] * clip_coef, m_w2[jj][2], v_w2[jj][2], ac);
+                        pw[jj][3] = adam_update(w4.w, g_w2[jj][3] * clip_coef, m_w2[jj][3], v_w2[jj][3], ac);
+                        *reinterpret_cast<float4*>(W2 + (4 * tj2 + jj) * H + 4 * tk2) =
+                            make_float4(pw[jj][0], pw[jj][1], pw[jj][2], pw[jj][3]);
                     }
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        *reinterpret_cast<float4*>(W2t + (4 * tk2 + kk) * H + 4 * (tj2 ^ tk2)) =
+                            make_float4(pw[0][kk], pw[1][kk], pw[2][kk], pw[3][kk]);
+                }
 #pragma unroll
                 for (int n = 0; n < NT1; ++n) {
                     const int t = tid + NTH * n, tk1 = t >> 4, tj1 = t & 15;
                     if (t < n_w1_tiles) {
 #pragma unroll
-                        for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {
-                                const int j = 4 * tj1 + jj, k = 4 * tk1 + kk;
-                                if (j < a.h0 && k < D)
-                                    W1t[k * H + j] = adam_update(W1t[k * H + j], g_w1[n][jj][kk] * clip_coef, m_w1[n][jj][kk],
-                                                                 v_w1[n][jj][kk], ac);
-                            }
+                        for (int kk = 0; kk < 4; ++kk) {
+                            float4* wp = reinterpret_cast<float4*>(W1t + (4 * tk1 + kk) * H + 4 * tj1);
+                            const float4 w4 = *wp;
+                            *wp = make_float4(adam_update(w4.x, g_w1[n][0][kk] * clip_coef, m_w1[n][0][kk], v_w1[n][0][kk], ac),
+                                              adam_update(w4.y, g_w1[n][1][kk] * clip_coef, m_w1[n][1][kk], v_w1[n][1][kk], ac),
+                                              adam_update(w4.z, g_w1[n][2][kk] * clip_coef, m_w1[n][2][kk], v_w1[n][2][kk], ac),
+                                              adam_update(w4.w, g_w1[n][3][kk] * clip_coef, m_w1[n][3][kk], v_w1[n][3][kk], ac));
+                        }
                     }
                 }
                 if (hd < AOUT) {
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const int k = 4 * hk4 + kk;
-                        if (k < a.h1)
-                            HW[hd * WA_LD + k] = adam_update(HW[hd * WA_LD + k], g_hw[kk] * clip_coef, m_hw[kk], v_hw[kk], ac);
-                    }
+                    float4* wp = reinterpret_cast<float4*>(HW + hd * WA_LD + 4 * hk4);
+                    const float4 w4 = *wp;
+                    *wp = make_float4(adam_update(w4.x, g_hw[0] * clip_coef, m_hw[0], v_hw[0], ac),
+                                      adam_update(w4.y, g_hw[1] * clip_coef, m_hw[1], v_hw[1], ac),
+                                      adam_update(w4.z, g_hw[2] * clip_coef, m_hw[2], v_hw[2], ac),
+                                      adam_update(w4.w, g_hw[3] * clip_coef, m_hw[3], v_hw[3], ac));
                 }
                 if (s_kind >= 0 && flat_scalar() >= 0) {
                     float* slot = s_kind == 0 ? &B1[s_idx] : s_kind == 1 ? &B2[s_idx] : s_kind == 2 ? &HB[s_idx] : &LOGSTD[s_idx];
-                    *slot = adam_update(*slot, g_s * clip_coef, m_s, v_s, ac);
+                    const float pnew = adam_update(*slot, g_s * clip_coef, m_s, v_s, ac);
+                    *slot = pnew;
+                    if (s_kind == 3) {
+                        const float sigma = expf(pnew);
+                        SIG[s_idx] = 1.f / (sigma * sigma);
+                        SIG[AMAX + s_idx] = logf(sigma);
+                    }
                 }
             }
+            ICRL_MARK(10)
             if (stop_rx == 1.f) { early_stop_epoch = epoch; stop_all = true; }
             if (stop_rx == 2.f) { stop_all = true; }
             // (the next chunk's leading __syncthreads orders these shared-memory weight updates before their first use)
         }  // minibatches
     }      // epochs
-    cp_async_wait_all();
+    if (working && cur_valid(cur)) mbar_wait(&BAR[q & 1], (uint32_t)((q >> 1) & 1));   // drain the in-flight prefetch
     __syncthreads();
+    if (timed) {
+        for (int i = 0; i < 16; ++i) a.timing[role * 16 + i] = tacc[i];
+    }
+#undef ICRL_MARK
 
     // ---- write back parameters and moments
     if (working) {
@@ -1096,24 +1151,54 @@ int icrl_ppo_train(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* pa
     a.step_before = adam_step_before;
     {
         const int total_steps = a.n_epochs * a.steps_per_epoch;
-        void *poff, *advstats;
-        if ((rc = icrl::device_scratch(icrl::SLOT_PPO0, (size_t)a.n_epochs * a.N * sizeof(int), &poff))) return rc;
-        if ((rc = icrl::device_scratch(icrl::SLOT_PPO1, (size_t)total_steps * 4 * sizeof(float), &advstats))) return rc;
-        icrl::ppo_prologue_kernel<<<total_steps, 128, 0, (cudaStream_t)stream>>>(
-            a.perm, (int*)poff, (float*)advstats, a.adv_r, a.adv_c, a.T, a.E, a.N, a.B, a.steps_per_epoch);
+        const long long n_rows = (long long)a.n_epochs * a.N, n_alloc = n_rows + icrl::RB;
+        const int aw = a.is_discrete ? 1 : a.A;
+        a.AP = (aw + 3) / 4 * 4;
+        void *xs, *as, *ss, *advstats;
+        if ((rc = icrl::device_scratch(icrl::SLOT_PPO0, (size_t)n_alloc * a.DP * 4, &xs))) return rc;
+        if ((rc = icrl::device_scratch(icrl::SLOT_PPO1, (size_t)total_steps * 8 * sizeof(float), &advstats))) return rc;
+        if ((rc = icrl::device_scratch(icrl::SLOT_PPO2, (size_t)n_alloc * a.AP * 4, &as))) return rc;
+        if ((rc = icrl::device_scratch(icrl::SLOT_PPO3, (size_t)n_alloc * 8 * 4, &ss))) return rc;
+        const long long blocks = (n_alloc + 7) / 8;
+        const int grid = (int)(blocks < 8LL * icrl::sm_count() ? blocks : 8LL * icrl::sm_count());
+        icrl::ppo_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, (float*)xs, (float*)as, (float*)ss, n_rows, n_alloc);
         ICRL_LAUNCH_CHECK();
-        a.poff = (const int*)poff;
+        icrl::ppo_stats_kernel<<<total_steps, 128, 0, (cudaStream_t)stream>>>((const float*)ss, (float*)advstats, a.N, a.B,
+                                                                             a.steps_per_epoch, a.beta1, a.beta2, a.lr,
+                                                                             a.step_before);
+        ICRL_LAUNCH_CHECK();
+        a.xs = (const float*)xs; a.as = (const float*)as; a.ss = (const float*)ss;
         a.advstats = (const float*)advstats;
     }
+    static unsigned long long* timing_dev = nullptr;
+    const bool want_timing = getenv("ICRL_PPO_TIMING") != nullptr;
+    if (want_timing && !timing_dev) cudaMalloc(&timing_dev, 48 * sizeof(unsigned long long));
+    a.timing = want_timing ? timing_dev : nullptr;
     const int n_tiles = 16 * (a.DP / 4);
     const int nt1 = (n_tiles + icrl::NTH - 1) / icrl::NTH;
     switch (nt1) {
-        case 1: return icrl::launch_ppo<1>(a, (cudaStream_t)stream);
-        case 2: return icrl::launch_ppo<2>(a, (cudaStream_t)stream);
-        case 3: return icrl::launch_ppo<3>(a, (cudaStream_t)stream);
+        case 1: rc = icrl::launch_ppo<1>(a, (cudaStream_t)stream); break;
+        case 2: rc = icrl::launch_ppo<2>(a, (cudaStream_t)stream); break;
+        case 3: rc = icrl::launch_ppo<3>(a, (cudaStream_t)stream); break;
+        default:
+            icrl::set_error("obs_dim %d too large for the PPO kernel (max 192)", a.D);
+            return ICRL_EUNSUPPORTED;
     }
-    icrl::set_error("obs_dim %d too large for the PPO kernel (max 192)", a.D);
-    return ICRL_EUNSUPPORTED;
+    if (rc == 0 && want_timing) {   // profiling aid: per-phase cycles of thread 0 of each trunk CTA (synchronises!)
+        unsigned long long h[48];
+        cudaStreamSynchronize((cudaStream_t)stream);
+        cudaMemcpy(h, timing_dev, sizeof(h), cudaMemcpyDeviceToHost);
+        const char* names[11] = {"wait+sync", "prefetch", "L1", "L2", "head", "headgrad+dH2", "dW2+dH1", "dW1", "reduce+stats",
+                                 "xchg+cluster", "adam"};
+        const double steps = (double)(a.max_steps > 0 ? a.max_steps : a.n_epochs * a.steps_per_epoch);
+        for (int r = 0; r < 3; ++r) {
+            fprintf(stderr, "[ppo timing] role %d cycles/step:", r);
+            double tot = 0;
+            for (int i = 0; i < 11; ++i) { fprintf(stderr, " %s=%.0f", names[i], h[r * 16 + i] / steps); tot += h[r * 16 + i] / steps; }
+            fprintf(stderr, " total=%.0f\n", tot);
+        }
+    }
+    return rc;
 }
 
 int icrl_policy_forward(const icrl_ppo_cfg* cfg, const float* params, const float* obs, int64_t n, float* head,
