@@ -3,53 +3,28 @@
 // Adam): per minibatch gather -> 3 tanh MLP forward -> losses -> backward -> global-norm clip -> Adam, for every
 // minibatch of every epoch, with the per-epoch target_kl early stop decided on the device.
 //
-// Why this shape.  The reference runs 1 600 *dependent* optimiser steps per rollout on 64-128 rows each: the path
-// is latency-bound, not HBM-bound (65 KB of algorithmic traffic per step).  So:
+// Why this shape.  The reference runs 1 600 *dependent* optimiser steps per rollout on 64-128 rows each: the path is
+// latency-bound, not HBM-bound (65 KB of algorithmic traffic per step).  So:
 //   * one launch; no host round trip between steps (the host only supplies numpy's permutations up front);
-//   * the three trunks (pi / vf / cvf) are independent networks (torch_layers.py:129-254), so each gets its own CTA
-//     of a 3-CTA cluster -- model parallel with NO activation exchange.  The only coupling is clip_grad_norm_'s
-//     global norm: one float per CTA per step, exchanged through distributed shared memory + a cluster barrier;
-//   * weights live in shared memory for the whole launch (k-major copies for the forward GEMMs, row-major W2 for
-//     the backward), Adam moments and the gradient live in REGISTERS: every thread owns fixed 4x4 tiles of W1/W2
-//     plus a few scalars for all 1 600 steps, so gradients are never materialised in memory;
-//   * the small GEMMs (64 x D x 64, 64 x 64 x 64) are FP32 FFMA with 4x4 register tiles and float4 broadcast
-//     shared-memory operand reads (fp32 tolerances of the north star rule out single-pass TF32/BF16 tensor cores).
-// Rollout data stay in the buffer's time-major layout; env-major minibatch indices are translated here.
-#include <math.h>
-#include <stdlib.h>
-
-#include "common.cuh"
+//   * the minibatch schedule is data-independent, so two massively parallel prologue kernels take everything that does
+//     not depend on the parameters out of the step chain: the random-access gather (minibatch-ordered streams in HBM),
+//     the per-minibatch advantage statistics and the Adam bias corrections;
+//   * the three trunks (pi / vf / cvf) are independent networks (torch_layers.py:129-254), so each gets its own CTA of a
+//     3-CTA cluster -- model parallel with NO activation exchange.  The only coupling is clip_grad_norm_'s global norm:
+//     one float per CTA per step, exchanged through distributed shared memory + a cluster barrier;
+//   * each 64-row chunk arrives by TMA bulk copies (cp.async.bulk + mbarrier) issued one chunk ahead by a single thread;
+//   * weights live in shared memory for the whole launch; Adam moments and the gradient live in REGISTERS: every thread
+//     owns fixed fragments of W1/W2 plus a few scalars for all 1 600 steps, so gradients are never materialised;
+//   * the five GEMMs per chunk (X W1^T, H1 W2^T, dH2 W2, dH2^T H1, dH1^T X) run on the tensor cores as mma.sync
+//     m16n8k8 TF32 with the 3xTF32 split (x = hi + lo; lo*hi + hi*lo + hi*hi), which keeps fp32-class accuracy
+//     (~2^-21) as the parity tolerances require.  Measured on B200: FFMA register tiles take 4.1k cycles per 64^3 GEMM
+//     (one 3-register FFMA per 2 cycles per SMSP), mma.sync TF32 sustains 512 FMA/cycle/SM -- see DESIGN.md.
+//     tcgen05 is not used here on purpose: M=64 tiles on a dependent chain of five tiny GEMMs would pay a TMEM
+//     allocate / commit / mbarrier / tcgen05.ld round trip per layer, and the epilogues (tanh, derivative masks, Adam)
+//     want the accumulators in registers.
+#include "k4_common.cuh"
 
 namespace icrl {
-
-constexpr int H = 64;          // padded hidden width (both layers)
-constexpr int RB = 64;         // rows per chunk
-constexpr int NTH = 256;       // threads per CTA
-constexpr int AMAX = 16;       // max action dims / discrete actions
-constexpr int LDH = 68;        // row stride of the activation tiles in the train kernel (bank-conflict-free float4 rows)
-constexpr int WA_LD = 68;      // leading dim of the action head weight in smem (bank-conflict-free float4 rows)
-constexpr float LOG_SQRT_2PI = 0.91893853320467274178f;
-constexpr float HALF_LOG_2PI_PLUS_HALF = 1.4189385332046727418f;
-
-struct PpoArgs {
-    int D, DP, A, is_discrete, h0, h1;
-    int T, E, N, B, n_epochs, steps_per_epoch, max_steps;
-    int has_target_kl, has_clip_vf_r, has_clip_vf_c;
-    float clip_range, clip_vf_r, clip_vf_c, ent_coef, vf_coef_r, vf_coef_c, max_grad_norm, nu;
-    double target_kl, lr, beta1, beta2, adam_eps;
-    long long step_before;
-    // flat parameter offsets (reference parameters() order)
-    int off_logstd, off_w1[3], off_b1[3], off_w2[3], off_b2[3], off_hw[3], off_hb[3];
-    const float *obs, *act, *old_logp, *old_vr, *adv_r, *ret_r, *old_vc, *adv_c, *ret_c;
-    const int* perm;
-    const float *xs, *as, *ss; // minibatch-ordered streams built by the prologue: obs [P][DP], actions [P][AP], scalars [P][8]
-    int AP;                    // padded action width of the stream (multiple of 4)
-    const float* advstats;    // [steps][8]: mean(adv_r), std(adv_r) (unbiased), mean(adv_c), 1/sqrt(1-b2^t), -lr/(1-b1^t)
-    const float* nu_dev;
-    float *params, *adam_m, *adam_v, *stats;
-    int* result;
-    unsigned long long* timing;   // optional [3 roles][16 phases] cycle accumulators (profiling aid)
-};
 
 // ---------------------------------------------------------------- cluster primitives (raw PTX)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -71,133 +46,88 @@ __device__ __forceinline__ void st_remote_f32(float* local_ptr, uint32_t rank, f
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
 }
 
-__device__ __forceinline__ void cp_async_4(void* dst_smem, const void* src_gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+// ---------------------------------------------------------------- tensor-core helpers (mma.sync m16n8k8, TF32, fp32 accumulate)
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    // hi = x with the 13 low mantissa bits cleared (one LOP3; cvt.rna.tf32 expands to a multi-instruction sequence and
+    // was 29% of all issued instructions), lo = x - hi exactly.  x = hi + lo holds exactly, hi is a valid TF32 value and
+    // the tensor core keeps 11 significant bits of lo (<= 2^-10 |x|): ~2^-20 relative per product, fp32-class.
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
 }
-__device__ __forceinline__ void cp_async_8(void* dst_smem, const void* src_gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
-__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src_gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// ---------------------------------------------------------------- block reductions (NTH threads)
-__device__ __forceinline__ float block_sum(float v, float* scratch) {
-    v = warp_sum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-    __syncthreads();
-    float t = 0.f;
+// One warp: C[16 x (8 per n-tile)] += A[16 x K] * B[K x .] with 3xTF32.
+//   A element (m, k) at A[m * sam + k * sak]   (A already points at the warp's first row / column)
+//   B element (k, n) at B[k * sbk + n * sbn]
+// n-tile i (i < NT, skipped when ncol0 + i * nstep >= nmax) covers columns ncol0 + i * nstep .. +7.
+// Fragment layout (PTX ISA, m16n8k8 .tf32): g = lane >> 2, t = lane & 3;
+//   a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);  b0 (k = t, n = g) b1 (k = t+4, n = g);
+//   c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
+template <int NT, int KC = 0>
+__device__ __forceinline__ void warp_gemm_3xtf32(float (&c)[NT][4], const float* __restrict__ A, int sam, int sak,
+                                                 const float* __restrict__ B, int sbk, int sbn, int K, int ncol0, int nstep,
+                                                 int nmax, int g, int t) {
+    const int kend = KC > 0 ? KC : K;   // KC > 0: compile-time K, fully unrolled so fragment loads run ahead of the MMAs
+#pragma unroll (KC > 0 ? KC / 8 : 2)
+    for (int k0 = 0; k0 < kend; k0 += 8) {
+        uint32_t ahi[4], alo[4];
+        {
+            const float* ap = A + (k0 + t) * sak + g * sam;
+            split_tf32(ap[0], ahi[0], alo[0]);
+            split_tf32(ap[8 * sam], ahi[1], alo[1]);
+            split_tf32(ap[4 * sak], ahi[2], alo[2]);
+            split_tf32(ap[4 * sak + 8 * sam], ahi[3], alo[3]);
+        }
 #pragma unroll
-    for (int i = 0; i < NTH / 32; ++i) t += scratch[i];
-    return t;
-}
-__device__ __forceinline__ double block_sum(double v, double* scratch) {
-    v = warp_sum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = 0.0;
-#pragma unroll
-    for (int i = 0; i < NTH / 32; ++i) t += scratch[i];
-    return t;
+        for (int i = 0; i < NT; ++i) {
+            const int n0 = ncol0 + i * nstep;
+            if (n0 < nmax) {
+                uint32_t bhi[2], blo[2];
+                const float* bp = B + (k0 + t) * sbk + (n0 + g) * sbn;
+                split_tf32(bp[0], bhi[0], blo[0]);
+                split_tf32(bp[4 * sbk], bhi[1], blo[1]);
+                mma_tf32(c[i], alo, bhi);
+                mma_tf32(c[i], ahi, blo);
+                mma_tf32(c[i], ahi, bhi);
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------- shared memory carve-up (float offsets)
 struct PpoSmem {
-    int w1t, w2t, w2, b1, b2, hw, hb, logstd, sig, x, h1, h2, dh, rowf, dmean, act, mu, rowoff, scratch, xch, total_bytes;
+    int w1, w2, b1, b2, hw, hb, logstd, sig, x, h1, h2, dh, rowf, dmean, act, mu, bar, scratch, xch, total_bytes;
 };
-__host__ __device__ inline PpoSmem ppo_smem_layout(int DP) {
+__host__ __device__ inline PpoSmem ppo_smem_layout(int LDX) {
     PpoSmem s;
     int o = 0;
-    s.w1t = o; o += DP * H;
-    s.w2t = o; o += H * H;
-    s.w2 = o; o += H * H;
+    s.w1 = o; o += H * LDX;          // W1[j][k], row stride LDX
+    s.w2 = o; o += H * LDH;          // W2[j][k], row stride LDH
     s.b1 = o; o += H;
     s.b2 = o; o += H;
     s.hw = o; o += AMAX * WA_LD;
     s.hb = o; o += AMAX;
     s.logstd = o; o += AMAX;
     s.sig = o; o += 2 * AMAX;        // per action dim: 1/sigma^2, log(sigma) -- refreshed by the thread that updates log_std
-    s.x = o; o += 2 * RB * DP;      // double buffered (cp.async prefetch of the next chunk)
+    s.x = o; o += 2 * RB * LDX;      // double buffered obs chunks (TMA destinations)
     s.h1 = o; o += RB * LDH;
     s.h2 = o; o += RB * LDH;
     s.dh = o; o += RB * LDH;
-    s.rowf = o; o += 2 * RB * 8;      // per-row scalars: 0 old_logp, 1 adv_r~, 2 adv_c~, 3 target return, 4 old value, 5 g/dV
+    s.rowf = o; o += 2 * RB * 8;     // per-row scalars of the stream: old_logp, adv_r, adv_c, ret_r, old_vr, ret_c, old_vc, (g)
     s.dmean = o; o += RB * AMAX;
     s.act = o; o += 2 * RB * AMAX;
     s.mu = o; o += RB * AMAX;        // action-head outputs (means / logits)
-    s.rowoff = o; o += 4;            // two 8-byte mbarriers (one per chunk buffer)
-    s.scratch = o; o += 64;         // 32 floats / 16 doubles of reduction scratch (8-byte aligned: o is even)
-    s.xch = o; o += 2 * 4 * 2;      // [parity][rank][{sumsq, stop}]
+    s.bar = o; o += 4;               // two 8-byte mbarriers (one per chunk buffer)
+    s.scratch = o; o += 128;
+    s.xch = o; o += 2 * 4 * 2;       // [parity][rank][{sumsq, stop}]
     s.total_bytes = o * 4;
     return s;
 }
-
-// 64x64 += A[64 x K] * Bt[K x 64]  (A row-major lda, Bt k-major ld 64); thread tile rows 4ty.., cols 4tx..
-// KC > 0: compile-time K (fully unrolled so operand loads run ahead of the FMAs); KC == 0: runtime K.
-// SWZ: Bt's float4 column slots are XOR-swizzled with (k >> 2) & 15 (the W2t copy: lets the Adam phase write the
-// transposed tile with conflict-free 128-bit stores while these row reads stay conflict-free).
-template <int KC, bool SWZ = false>
-__device__ __forceinline__ void gemm_tile_4x4(float (&acc)[4][4], const float* __restrict__ A, int lda,
-                                              const float* __restrict__ Bt, int K, int ty, int tx) {
-    const float* a0 = A + (4 * ty) * lda;
-    const float* b0 = Bt + 4 * tx;
-    const int kend = KC > 0 ? KC : K;
-#pragma unroll (KC > 0 ? KC / 4 : 2)
-    for (int k = 0; k < kend; k += 4) {
-        float4 a[4], w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + i * lda + k);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-            w[kk] = SWZ ? *reinterpret_cast<const float4*>(Bt + (k + kk) * H + 4 * (tx ^ ((k >> 2) & 15)))
-                        : *reinterpret_cast<const float4*>(b0 + (k + kk) * H);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
-                acc[i][0] = fmaf(av, w[kk].x, acc[i][0]);
-                acc[i][1] = fmaf(av, w[kk].y, acc[i][1]);
-                acc[i][2] = fmaf(av, w[kk].z, acc[i][2]);
-                acc[i][3] = fmaf(av, w[kk].w, acc[i][3]);
-            }
-        }
-    }
-}
-
-// acc[jj][kk] += sum_r L[r][4tj+jj] * R[r][4tk+kk]   (both row-major; reduction over the chunk's rows)
-__device__ __forceinline__ void outer_tile_4x4(float (&acc)[4][4], const float* __restrict__ L, int ldl,
-                                               const float* __restrict__ R, int ldr, int tj, int tk) {
-    const float* l0 = L + 4 * tj;
-    const float* r0 = R + 4 * tk;
-#pragma unroll 8
-    for (int r = 0; r < RB; ++r) {      // padding rows of the chunk hold zero gradients, so the trip count is fixed
-        const float4 d = *reinterpret_cast<const float4*>(l0 + r * ldl);
-        const float4 h = *reinterpret_cast<const float4*>(r0 + r * ldr);
-        acc[0][0] = fmaf(d.x, h.x, acc[0][0]); acc[0][1] = fmaf(d.x, h.y, acc[0][1]);
-        acc[0][2] = fmaf(d.x, h.z, acc[0][2]); acc[0][3] = fmaf(d.x, h.w, acc[0][3]);
-        acc[1][0] = fmaf(d.y, h.x, acc[1][0]); acc[1][1] = fmaf(d.y, h.y, acc[1][1]);
-        acc[1][2] = fmaf(d.y, h.z, acc[1][2]); acc[1][3] = fmaf(d.y, h.w, acc[1][3]);
-        acc[2][0] = fmaf(d.z, h.x, acc[2][0]); acc[2][1] = fmaf(d.z, h.y, acc[2][1]);
-        acc[2][2] = fmaf(d.z, h.z, acc[2][2]); acc[2][3] = fmaf(d.z, h.w, acc[2][3]);
-        acc[3][0] = fmaf(d.w, h.x, acc[3][0]); acc[3][1] = fmaf(d.w, h.y, acc[3][1]);
-        acc[3][2] = fmaf(d.w, h.z, acc[3][2]); acc[3][3] = fmaf(d.w, h.w, acc[3][3]);
-    }
-}
-
-// (unused: measured no gain, kept for reference) tanh(x) = 1 - 2 / (1 + e^{2x}) on the SFU (ex2.approx + rcp.approx): ~7 instructions instead of tanhf's ~30, absolute
-// error <= 2e-7 (about 2 ulp of 1.0), saturates correctly to +-1 for large |x|.
-__device__ __forceinline__ float tanh_fast(float x) {
-    const float e = __expf(2.f * x);
-    return 1.f - __fdividef(2.f, 1.f + e);
-}
-
-// physical column of element (k, j) in the swizzled transposed copy W2t[k][.]
-__device__ __forceinline__ int w2t_col(int k, int j) { return (((j >> 2) ^ ((k >> 2) & 15)) << 2) | (j & 3); }
 
 // one Adam update in torch's single-tensor form (torch/optim/adam.py); returns the new parameter
 struct AdamConsts {
@@ -291,35 +221,45 @@ __global__ void __launch_bounds__(128) ppo_stats_kernel(const float* __restrict_
     }
 }
 
+// ---------------------------------------------------------------- the persistent train kernel
+constexpr int NTT = 256;       // threads of the train kernel: 8 warps (16 warps measured slower: 31.4k vs 27.5k cycles/step on HC)
+constexpr int NWT = NTT / 32;
+constexpr int NTW2 = 4;        // n-tiles of a 64 x 64 output per warp (warp tile 16 x 32)
+// NT1 = n-tiles of dW1 (64 x KP) each warp owns (warp w: m-tile w & 3, n-tiles (w >> 2) + 2 i).
 template <int NT1>
-__global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant__ PpoArgs a) {
+__global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant__ PpoArgs a) {
     extern __shared__ __align__(16) float sm[];
     const float nu = a.nu_dev ? *a.nu_dev : a.nu;
-    const PpoSmem L = ppo_smem_layout(a.DP);
-    const int tid = threadIdx.x;
+    const int LDX = a.DP, KP = a.KP, D = a.D;
+    const PpoSmem L = ppo_smem_layout(LDX);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int role = (int)cluster_ctarank();        // 0 pi, 1 vf, 2 cvf, >=3 idle (only joins the barriers)
     const int ncta = (int)cluster_nctarank();
     const bool working = role < 3;
     const int trunk = working ? role : 0;
-    const int D = a.D, DP = a.DP;
     const int AOUT = (role == 0) ? a.A : 1;
     const bool has_logstd = (role == 0) && !a.is_discrete;
 
-    float* W1t = sm + L.w1t; float* W2t = sm + L.w2t; float* W2 = sm + L.w2;
+    float* W1 = sm + L.w1; float* W2 = sm + L.w2;
     float* B1 = sm + L.b1; float* B2 = sm + L.b2; float* HW = sm + L.hw; float* HB = sm + L.hb;
     float* LOGSTD = sm + L.logstd; float* SIG = sm + L.sig;
     float* X = sm + L.x; float* H1 = sm + L.h1; float* H2 = sm + L.h2; float* DH = sm + L.dh;
     float* ROWF = sm + L.rowf; float* DMEAN = sm + L.dmean; float* ACT = sm + L.act; float* MU = sm + L.mu;
-    uint64_t* BAR = reinterpret_cast<uint64_t*>(sm + L.rowoff);
+    uint64_t* BAR = reinterpret_cast<uint64_t*>(sm + L.bar);
     float* scratch = sm + L.scratch;
     float* XCH = sm + L.xch;
 
-    // ---- thread -> parameter ownership (fixed for the whole launch)
-    const int tj2 = tid >> 4, tk2 = tid & 15;                 // W2 tile: rows j = 4*tj2.., cols k = 4*tk2..
-    const int n_w1_tiles = 16 * (DP / 4);
-    const int hd = tid >> 4, hk4 = tid & 15;                  // head weight: row hd, cols 4*hk4..
-    // scalar slot: b1 | b2 | head bias | log_std
-    int s_kind = -1, s_idx = 0;
+    // ---- warp tiling of every 64 x 64 (or 64 x KP) GEMM output, and the parameter ownership that follows from it
+    const int g = lane >> 2, t = lane & 3;          // mma fragment coordinates
+    const int mt = warp & 3, ng = warp >> 2;        // warp's m-tile (16 rows) and n-group (32 columns of a 64-wide output)
+    // W2[j][k] owned by this thread: j = 16 mt + g (+8), k = 32 ng + 8 nt + 2 t (+1), nt < 4     -> [nt][c] as the C fragment
+    // W1[j][k] owned by this thread: j as above,        k = 8 (ng + 2 i) + 2 t (+1),  i < NT1   (valid while k < KP)
+    const int oj = 16 * mt + g;
+    auto w2_k = [&](int nt) { return 32 * ng + 8 * nt + 2 * t; };
+    auto w1_k = [&](int i) { return 8 * (ng + 2 * i) + 2 * t; };
+    const bool lowhalf = tid < 256;                 // head / per-row phases use 256 threads (4 per row)
+    const int hd = lowhalf ? (tid >> 4) : AMAX, hk4 = tid & 15;   // head weight: row hd, cols 4*hk4..
+    int s_kind = -1, s_idx = 0;                     // scalar slot: b1 | b2 | head bias | log_std
     if (tid < 64) { s_kind = 0; s_idx = tid; }
     else if (tid < 128) { s_kind = 1; s_idx = tid - 64; }
     else if (tid < 128 + AOUT) { s_kind = 2; s_idx = tid - 128; }
@@ -337,56 +277,60 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
         }
         return -1;
     };
+    // element c of an owned fragment -> (row, column offset)
+    auto frag_j = [&](int c) { return oj + ((c & 2) ? 8 : 0); };
+    auto frag_dk = [&](int c) { return c & 1; };
 
-    // Adam moments in registers
-    float m_w2[4][4], v_w2[4][4], m_w1[NT1][4][4], v_w1[NT1][4][4], m_hw[4], v_hw[4], m_s = 0.f, v_s = 0.f;
-    // ---- load parameters into shared memory (zero padded) and moments into registers
-    for (int i = tid; i < DP * H; i += NTH) W1t[i] = 0.f;
-    for (int i = tid; i < H * H; i += NTH) { W2t[i] = 0.f; W2[i] = 0.f; }
-    for (int i = tid; i < AMAX * WA_LD; i += NTH) HW[i] = 0.f;
+    // ---- parameters -> shared memory (zero padded), Adam moments -> registers
+    float m_w2[NTW2][4], v_w2[NTW2][4], m_w1[NT1][4], v_w1[NT1][4], m_hw[4], v_hw[4], m_s = 0.f, v_s = 0.f;
+    for (int i = tid; i < H * LDX; i += NTT) {
+        const int j = i / LDX, k = i - j * LDX;
+        const int f = working ? flat_w1(j, k) : -1;
+        W1[i] = f >= 0 ? a.params[f] : 0.f;
+    }
+    for (int i = tid; i < H * LDH; i += NTT) {
+        const int j = i / LDH, k = i - j * LDH;
+        const int f = (working && k < H) ? flat_w2(j, k) : -1;
+        W2[i] = f >= 0 ? a.params[f] : 0.f;
+    }
+    for (int i = tid; i < AMAX * WA_LD; i += NTT) {
+        const int d = i / WA_LD, k = i - d * WA_LD;
+        const int f = working ? flat_hw(d, k) : -1;
+        HW[i] = f >= 0 ? a.params[f] : 0.f;
+    }
     if (tid < H) { B1[tid] = 0.f; B2[tid] = 0.f; }
     if (tid < AMAX) { HB[tid] = 0.f; LOGSTD[tid] = 0.f; }
     if (tid < 16) XCH[tid] = 0.f;
     __syncthreads();
+#pragma unroll
+    for (int nt = 0; nt < NTW2; ++nt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int f = working ? flat_w2(frag_j(c), w2_k(nt) + frag_dk(c)) : -1;
+            m_w2[nt][c] = f >= 0 ? a.adam_m[f] : 0.f;
+            v_w2[nt][c] = f >= 0 ? a.adam_v[f] : 0.f;
+        }
+#pragma unroll
+    for (int i = 0; i < NT1; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int f = working ? flat_w1(frag_j(c), w1_k(i) + frag_dk(c)) : -1;
+            m_w1[i][c] = f >= 0 ? a.adam_m[f] : 0.f;
+            v_w1[i][c] = f >= 0 ? a.adam_v[f] : 0.f;
+        }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        const int f = working ? flat_hw(hd, 4 * hk4 + kk) : -1;
+        m_hw[kk] = f >= 0 ? a.adam_m[f] : 0.f;
+        v_hw[kk] = f >= 0 ? a.adam_v[f] : 0.f;
+    }
     if (working) {
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                const int j = 4 * tj2 + jj, k = 4 * tk2 + kk, f = flat_w2(j, k);
-                m_w2[jj][kk] = f >= 0 ? a.adam_m[f] : 0.f;
-                v_w2[jj][kk] = f >= 0 ? a.adam_v[f] : 0.f;
-                if (f >= 0) { const float w = a.params[f]; W2[j * H + k] = w; W2t[k * H + w2t_col(k, j)] = w; }
-            }
-#pragma unroll
-        for (int n = 0; n < NT1; ++n) {
-            const int t = tid + NTH * n, tk1 = t >> 4, tj1 = t & 15;
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const int j = 4 * tj1 + jj, k = 4 * tk1 + kk;
-                    const int f = (t < n_w1_tiles) ? flat_w1(j, k) : -1;
-                    m_w1[n][jj][kk] = f >= 0 ? a.adam_m[f] : 0.f;
-                    v_w1[n][jj][kk] = f >= 0 ? a.adam_v[f] : 0.f;
-                    if (f >= 0) W1t[k * H + j] = a.params[f];
-                }
-        }
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-            const int f = flat_hw(hd, 4 * hk4 + kk);
-            m_hw[kk] = f >= 0 ? a.adam_m[f] : 0.f;
-            v_hw[kk] = f >= 0 ? a.adam_v[f] : 0.f;
-            if (f >= 0) HW[hd * WA_LD + 4 * hk4 + kk] = a.params[f];
-        }
-        {
-            const int f = flat_scalar();
-            if (f >= 0) {
-                m_s = a.adam_m[f]; v_s = a.adam_v[f];
-                const float p = a.params[f];
-                if (s_kind == 0) B1[s_idx] = p; else if (s_kind == 1) B2[s_idx] = p;
-                else if (s_kind == 2) HB[s_idx] = p; else LOGSTD[s_idx] = p;
-            }
+        const int f = flat_scalar();
+        if (f >= 0) {
+            m_s = a.adam_m[f]; v_s = a.adam_v[f];
+            const float p = a.params[f];
+            if (s_kind == 0) B1[s_idx] = p; else if (s_kind == 1) B2[s_idx] = p;
+            else if (s_kind == 2) HB[s_idx] = p; else LOGSTD[s_idx] = p;
         }
     }
     __syncthreads();
@@ -395,15 +339,16 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
         SIG[tid] = 1.f / (sigma * sigma);
         SIG[AMAX + tid] = logf(sigma);
     }
+    if (tid == 0) {
+        mbar_init(&BAR[0], 1);
+        mbar_init(&BAR[1], 1);
+        fence_mbar_init();
+    }
     __syncthreads();
     cluster_sync_all();   // every CTA has zeroed its exchange slots before any peer writes into them
 
-    const int ty = tid >> 4, tx = tid & 15;     // forward tile: rows 4ty.., cols 4tx..
     const int hr = tid >> 2, hq = tid & 3;      // head mapping: row hr, quarter hq
-    const int warp = tid >> 5, lane = tid & 31;
-    const int aw = a.is_discrete ? 1 : a.A;
-    // widest cp.async the obs rows allow (row stride D floats, 16-byte aligned base)
-    const int xvec = ((reinterpret_cast<uintptr_t>(a.obs) & 15) == 0) ? ((D % 4 == 0) ? 4 : (D % 2 == 0) ? 2 : 1) : 1;
+    const int AP = a.AP;
 
     // ---- chunk pipeline: chunk q+1 of the minibatch-ordered streams is fetched by TMA bulk copies (one elected thread,
     // completion on an mbarrier) while chunk q is being computed.  No global latency is exposed to the step chain.
@@ -415,25 +360,18 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
         if (c.c0 >= cur_bn(c)) { c.c0 = 0; if (++c.mb >= a.steps_per_epoch) { c.mb = 0; ++c.epoch; } }
         return c;
     };
-    const int AP = a.AP;
     auto fetch_chunk = [&](const Cursor& c, int buf) {   // called by thread 0 only
         const size_t p = (size_t)c.epoch * a.N + (size_t)c.mb * a.B + c.c0;   // streams carry RB rows of tail padding
-        const uint32_t xb = RB * DP * 4, sb = RB * 8 * 4, ab = (role == 0) ? RB * AP * 4 : 0;
+        const uint32_t xb = RB * LDX * 4, sb = RB * 8 * 4, ab = (role == 0) ? RB * AP * 4 : 0;
         fence_proxy_async();   // earlier generic-proxy accesses to this buffer are ordered before the async-proxy writes
         mbar_expect_tx(&BAR[buf], xb + sb + ab);
-        bulk_g2s(X + buf * RB * DP, a.xs + p * DP, xb, &BAR[buf]);
+        bulk_g2s(X + buf * RB * LDX, a.xs + p * LDX, xb, &BAR[buf]);
         bulk_g2s(ROWF + buf * RB * 8, a.ss + p * 8, sb, &BAR[buf]);
         if (role == 0) bulk_g2s(ACT + buf * RB * AMAX, a.as + p * AP, ab, &BAR[buf]);
     };
 
     Cursor cur = {0, 0, 0};
     int q = 0;                                   // running chunk counter (buffer parity / mbarrier phase)
-    if (tid == 0) {
-        mbar_init(&BAR[0], 1);
-        mbar_init(&BAR[1], 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
     if (working && tid == 0) fetch_chunk(cur, 0);
 
     int step = 0, early_stop_epoch = a.n_epochs;
@@ -459,21 +397,21 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
             const int Bn = min(a.B, a.N - mb * a.B);
             const float invB = 1.0f / (float)Bn;
 
-            // gradient accumulators (registers)
-            float g_w2[4][4], g_w1[NT1][4][4], g_hw[4], g_s = 0.f;
+            // gradient accumulators (registers, mma C-fragment layout)
+            float g_w2[NTW2][4], g_w1[NT1][4], g_hw[4], g_s = 0.f;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                g_hw[i] = 0.f;
+            for (int i = 0; i < 4; ++i) g_hw[i] = 0.f;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    g_w2[i][j] = 0.f;
+            for (int i = 0; i < NTW2; ++i)
 #pragma unroll
-                    for (int n = 0; n < NT1; ++n) g_w1[n][i][j] = 0.f;
-                }
-            }
+                for (int c = 0; c < 4; ++c) g_w2[i][c] = 0.f;
+#pragma unroll
+            for (int i = 0; i < NT1; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) g_w1[i][c] = 0.f;
             // loss partial sums (thread-local, one merged block reduction at the end of the step)
             float s_a = 0.f, s_b = 0.f, s_c = 0.f, s_d = 0.f, s_e = 0.f;
-            // minibatch statistics of the advantages (ppo_lag.py:218-222) from the prologue kernel's table
+            // minibatch statistics of the advantages (ppo_lag.py:218-222) and Adam constants from the prologue's table
             const float adv_mean_r = a.advstats[step * 8 + 0], adv_std_r = a.advstats[step * 8 + 1],
                         adv_mean_c = a.advstats[step * 8 + 2];
             const float adam_inv_bc2_sqrt = a.advstats[step * 8 + 3], adam_neg_step = a.advstats[step * 8 + 4];
@@ -482,7 +420,7 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                 for (int c0 = 0; c0 < Bn; c0 += RB, ++q) {
                     const int rows = min(RB, Bn - c0);
                     const int buf = q & 1;
-                    const float* Xc = X + buf * RB * DP;
+                    const float* Xc = X + buf * RB * LDX;
                     float* Rc = ROWF + buf * RB * 8;
                     const float* Ac = ACT + buf * RB * AMAX;   // rows at stride AP (as the stream stores them)
                     mbar_wait(&BAR[buf], (uint32_t)((q >> 1) & 1));
@@ -494,39 +432,46 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                         cur = nxt;
                     }
                     ICRL_MARK(1)
-                    // ---- forward layer 1: H1 = tanh(X W1^T + b1)
+
+                    // ---- forward layer 1: H1 = tanh(X W1^T + b1)          [warp tile: rows 16mt.., cols 32ng..]
                     {
-                        float acc[4][4];
+                        float acc[NTW2][4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
+                        for (int nt = 0; nt < NTW2; ++nt) {
+                            const float2 b = *reinterpret_cast<const float2*>(B1 + w2_k(nt));
+                            acc[nt][0] = b.x; acc[nt][1] = b.y; acc[nt][2] = b.x; acc[nt][3] = b.y;
+                        }
+                        warp_gemm_3xtf32<NTW2>(acc, Xc + 16 * mt * LDX, LDX, 1, W1, 1, LDX, KP, 32 * ng, 8, H, g, t);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) acc[i][j] = B1[4 * tx + j];
-                        gemm_tile_4x4<0>(acc, Xc, DP, W1t, DP, ty, tx);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            *reinterpret_cast<float4*>(H1 + (4 * ty + i) * LDH + 4 * tx) =
-                                make_float4(tanhf(acc[i][0]), tanhf(acc[i][1]), tanhf(acc[i][2]), tanhf(acc[i][3]));
+                        for (int nt = 0; nt < NTW2; ++nt) {
+                            *reinterpret_cast<float2*>(H1 + oj * LDH + w2_k(nt)) = make_float2(tanhf(acc[nt][0]), tanhf(acc[nt][1]));
+                            *reinterpret_cast<float2*>(H1 + (oj + 8) * LDH + w2_k(nt)) = make_float2(tanhf(acc[nt][2]), tanhf(acc[nt][3]));
+                        }
                     }
                     __syncthreads();
                     ICRL_MARK(2)
                     // ---- forward layer 2: H2 = tanh(H1 W2^T + b2)
                     {
-                        float acc[4][4];
+                        float acc[NTW2][4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
+                        for (int nt = 0; nt < NTW2; ++nt) {
+                            const float2 b = *reinterpret_cast<const float2*>(B2 + w2_k(nt));
+                            acc[nt][0] = b.x; acc[nt][1] = b.y; acc[nt][2] = b.x; acc[nt][3] = b.y;
+                        }
+                        warp_gemm_3xtf32<NTW2, H>(acc, H1 + 16 * mt * LDH, LDH, 1, W2, 1, LDH, H, 32 * ng, 8, H, g, t);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) acc[i][j] = B2[4 * tx + j];
-                        gemm_tile_4x4<H, true>(acc, H1, LDH, W2t, H, ty, tx);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            *reinterpret_cast<float4*>(H2 + (4 * ty + i) * LDH + 4 * tx) =
-                                make_float4(tanhf(acc[i][0]), tanhf(acc[i][1]), tanhf(acc[i][2]), tanhf(acc[i][3]));
+                        for (int nt = 0; nt < NTW2; ++nt) {
+                            *reinterpret_cast<float2*>(H2 + oj * LDH + w2_k(nt)) = make_float2(tanhf(acc[nt][0]), tanhf(acc[nt][1]));
+                            *reinterpret_cast<float2*>(H2 + (oj + 8) * LDH + w2_k(nt)) = make_float2(tanhf(acc[nt][2]), tanhf(acc[nt][3]));
+                        }
                     }
                     __syncthreads();
-
                     ICRL_MARK(3)
+
                     // ---- heads + losses + d(loss)/d(head output).  4 threads per row (hr, hq).
-                    if (role == 0) {
+                    if (!lowhalf) {
+                        // warps 8-15 have no per-row work in the head phase
+                    } else if (role == 0) {
                         // action head: outputs d = hq, hq+4, hq+8, hq+12
                         float out[4];
 #pragma unroll
@@ -618,9 +563,9 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                         else if (pl1 > pl2) wgt = inrange ? 1.f : 0.f;
                         else wgt = 0.5f + (inrange ? 0.5f : 0.f);
                         const float inv1pnu = 1.f / (1.f + nu);
-                        float g = 0.f;
+                        float gl = 0.f;
                         if (valid) {
-                            g = ratio * (-A_r * wgt + nu * A_c) * invB * inv1pnu;      // dL/dlogp
+                            gl = ratio * (-A_r * wgt + nu * A_c) * invB * inv1pnu;       // dL/dlogp
                             if (hq == 0) {
                                 s_a += fminf(pl1, pl2);                                   // sum min(pl1, pl2)
                                 s_b += A_c * ratio;                                       // sum cost_adv * ratio
@@ -633,9 +578,9 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const int d = hq + 4 * u;
-                            if (d < AMAX) DMEAN[hr * AMAX + d] = (d < a.A) ? (g * dcoef[u] + ge * dent[u]) : 0.f;
+                            if (d < AMAX) DMEAN[hr * AMAX + d] = (d < a.A) ? (gl * dcoef[u] + ge * dent[u]) : 0.f;
                         }
-                        if (hq == 0) Rc[hr * 8 + 7] = g;
+                        if (hq == 0) Rc[hr * 8 + 7] = gl;
                     } else {
                         // value head: partial dot over k in [16hq, 16hq+16)
                         float acc = 0.f;
@@ -669,8 +614,8 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                         if (hq == 0) { DMEAN[hr * AMAX + 0] = dV; }
                     }
                     __syncthreads();
-
                     ICRL_MARK(4)
+
                     // ---- head weight / bias / log_std gradients (rows beyond `rows` carry zero dmean: loops run over RB)
                     if (hd < AOUT) {
                         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
@@ -700,7 +645,7 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                         g_s += acc - a.ent_coef * (float)rows * invB;
                     }
                     // ---- dH2pre[r][k] = (sum_d dmean[r][d] * HW[d][k]) * (1 - H2^2)   (thread: row hr, k in [16hq,16hq+16))
-                    {
+                    if (lowhalf) {
                         float dloc[16];
 #pragma unroll
                         for (int k = 0; k < 16; ++k) dloc[k] = 0.f;
@@ -726,39 +671,38 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                         }
                     }
                     __syncthreads();
-
                     ICRL_MARK(5)
-                    // ---- dW2 += dH2pre^T H1 ; db2 ; dH1pre = (dH2pre W2) * (1 - H1^2) -> written over H2
-                    outer_tile_4x4(g_w2, DH, LDH, H1, LDH, tj2, tk2);
-                    if (s_kind == 1) {
+
+                    // ---- dW2[j][k] += sum_r dH2pre[r][j] H1[r][k]   (A = dH2pre^T read in place, B = H1)
+                    warp_gemm_3xtf32<NTW2, RB>(g_w2, DH + 16 * mt, 1, LDH, H1, LDH, 1, RB, 32 * ng, 8, H, g, t);
+                    if (s_kind == 1) {                                   // db2
                         float acc = 0.f;
 #pragma unroll 8
                         for (int r = 0; r < RB; ++r) acc += DH[r * LDH + s_idx];
                         g_s += acc;
                     }
+                    // ---- dH1pre = (dH2pre W2) * (1 - H1^2) -> written over H2      (B[k = j][n = k] = W2[j][k] read in place)
                     {
-                        float acc[4][4];
+                        float acc[NTW2][4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
+                        for (int nt = 0; nt < NTW2; ++nt)
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-                        gemm_tile_4x4<H>(acc, DH, LDH, W2, H, ty, tx);   // sum_j dH2[r][j] * W2[j][k]  (W2 row-major == "k-major" in j)
+                            for (int c = 0; c < 4; ++c) acc[nt][c] = 0.f;
+                        warp_gemm_3xtf32<NTW2, H>(acc, DH + 16 * mt * LDH, LDH, 1, W2, LDH, 1, H, 32 * ng, 8, H, g, t);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float4 h = *reinterpret_cast<const float4*>(H1 + (4 * ty + i) * LDH + 4 * tx);
-                            *reinterpret_cast<float4*>(H2 + (4 * ty + i) * LDH + 4 * tx) =
-                                make_float4(acc[i][0] * (1.f - h.x * h.x), acc[i][1] * (1.f - h.y * h.y),
-                                            acc[i][2] * (1.f - h.z * h.z), acc[i][3] * (1.f - h.w * h.w));
+                        for (int nt = 0; nt < NTW2; ++nt) {
+                            const float2 ha = *reinterpret_cast<const float2*>(H1 + oj * LDH + w2_k(nt));
+                            const float2 hb = *reinterpret_cast<const float2*>(H1 + (oj + 8) * LDH + w2_k(nt));
+                            *reinterpret_cast<float2*>(H2 + oj * LDH + w2_k(nt)) =
+                                make_float2(acc[nt][0] * (1.f - ha.x * ha.x), acc[nt][1] * (1.f - ha.y * ha.y));
+                            *reinterpret_cast<float2*>(H2 + (oj + 8) * LDH + w2_k(nt)) =
+                                make_float2(acc[nt][2] * (1.f - hb.x * hb.x), acc[nt][3] * (1.f - hb.y * hb.y));
                         }
                     }
                     __syncthreads();
                     ICRL_MARK(6)
-                    // ---- dW1 += dH1pre^T X ; db1
-#pragma unroll
-                    for (int n = 0; n < NT1; ++n) {
-                        const int t = tid + NTH * n;
-                        if (t < n_w1_tiles) outer_tile_4x4(g_w1[n], H2, LDH, Xc, DP, t & 15, t >> 4);
-                    }
+                    // ---- dW1[j][k] += sum_r dH1pre[r][j] X[r][k] ; db1
+                    warp_gemm_3xtf32<NT1, RB>(g_w1, H2 + 16 * mt, 1, LDH, Xc, LDX, 1, RB, 8 * ng, 16, KP, g, t);
                     if (s_kind == 0) {
                         float acc = 0.f;
 #pragma unroll 8
@@ -773,15 +717,15 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
             float ss = 0.f;
             if (working) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    ss = fmaf(g_hw[i], g_hw[i], ss);
+                for (int i = 0; i < 4; ++i) ss = fmaf(g_hw[i], g_hw[i], ss);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        ss = fmaf(g_w2[i][j], g_w2[i][j], ss);
+                for (int i = 0; i < NTW2; ++i)
 #pragma unroll
-                        for (int n = 0; n < NT1; ++n) ss = fmaf(g_w1[n][i][j], g_w1[n][i][j], ss);
-                    }
-                }
+                    for (int c = 0; c < 4; ++c) ss = fmaf(g_w2[i][c], g_w2[i][c], ss);
+#pragma unroll
+                for (int i = 0; i < NT1; ++i)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) ss = fmaf(g_w1[i][c], g_w1[i][c], ss);
                 ss = fmaf(g_s, g_s, ss);
             }
             float red[6] = {s_a, s_b, s_c, s_d, s_e, ss};
@@ -794,10 +738,10 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
             __syncthreads();
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
-                float t = 0.f;
+                float tsum = 0.f;
 #pragma unroll
-                for (int wv = 0; wv < NTH / 32; ++wv) t += scratch[wv * 8 + i];
-                red[i] = t;
+                for (int wv = 0; wv < NWT; ++wv) tsum += scratch[wv * 8 + i];
+                red[i] = tsum;
             }
             ss = red[5];
             const size_t so = (size_t)step * ICRL_PPO_STATS_PER_STEP;
@@ -816,8 +760,8 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
             } else if (working) {
                 if (tid == 0) a.stats[so + (role == 1 ? 2 : 3)] = red[0] * invB;
             }
-
             ICRL_MARK(8)
+
             // ---- global gradient norm: local sum of squares -> DSMEM exchange -> cluster barrier
             // epoch-level KL early stop is decided by the pi CTA right here (it has this step's KL) and rides along
             float stop_flag = 0.f;
@@ -843,7 +787,7 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                 a.stats[so + 6] = 0.f;   // total loss is assembled on the host from the parts (needs all three CTAs)
             }
 
-            // ---- Adam (each thread updates the parameters it owns; smem copies refreshed in place)
+            // ---- Adam (each thread updates the parameters it owns; the shared-memory weights are refreshed in place)
             if (working) {
                 AdamConsts ac;
                 ac.one_minus_b1 = (float)(1.0 - a.beta1);
@@ -852,38 +796,27 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
                 ac.inv_bc2_sqrt = adam_inv_bc2_sqrt;
                 ac.eps = (float)a.adam_eps;
                 ac.neg_step_size = adam_neg_step;
-                {
-                    // W2 tile (rows 4tj2.., cols 4tk2..): 128-bit reads/writes of the row-major copy, 128-bit swizzled
-                    // writes of the transposed copy.  Padding entries (j >= h1 or k >= h0) keep g = m = v = 0 and stay 0.
-                    float pw[4][4];
+                // padding entries (j >= h1, k >= h0 / D) keep g = m = v = 0 and therefore stay exactly 0
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const float4 w4 = *reinterpret_cast<const float4*>(W2 + (4 * tj2 + jj) * H + 4 * tk2);
-                        pw[jj][0] = adam_update(w4.x, g_w2[jj][0] * clip_coef, m_w2[jj][0], v_w2[jj][0], ac);
-                        pw[jj][1] = adam_update(w4.y, g_w2[jj][1] * clip_coef, m_w2[jj][1], v_w2[jj][1], ac);
-                        pw[jj][2] = adam_update(w4.z, g_w2[jj][2] * clip_coef, m_w2[jj][2], v_w2[jj][2], ac);
-                        pw[jj][3] = adam_update(w4.w, g_w2[jj][3] * clip_coef, m_w2[jj][3], v_w2[jj][3], ac);
-                        *reinterpret_cast<float4*>(W2 + (4 * tj2 + jj) * H + 4 * tk2) =
-                            make_float4(pw[jj][0], pw[jj][1], pw[jj][2], pw[jj][3]);
-                    }
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        *reinterpret_cast<float4*>(W2t + (4 * tk2 + kk) * H + 4 * (tj2 ^ tk2)) =
-                            make_float4(pw[0][kk], pw[1][kk], pw[2][kk], pw[3][kk]);
+                for (int nt = 0; nt < NTW2; ++nt) {
+                    float2* pa = reinterpret_cast<float2*>(W2 + oj * LDH + w2_k(nt));
+                    float2* pb = reinterpret_cast<float2*>(W2 + (oj + 8) * LDH + w2_k(nt));
+                    const float2 wa = *pa, wb = *pb;
+                    *pa = make_float2(adam_update(wa.x, g_w2[nt][0] * clip_coef, m_w2[nt][0], v_w2[nt][0], ac),
+                                      adam_update(wa.y, g_w2[nt][1] * clip_coef, m_w2[nt][1], v_w2[nt][1], ac));
+                    *pb = make_float2(adam_update(wb.x, g_w2[nt][2] * clip_coef, m_w2[nt][2], v_w2[nt][2], ac),
+                                      adam_update(wb.y, g_w2[nt][3] * clip_coef, m_w2[nt][3], v_w2[nt][3], ac));
                 }
 #pragma unroll
-                for (int n = 0; n < NT1; ++n) {
-                    const int t = tid + NTH * n, tk1 = t >> 4, tj1 = t & 15;
-                    if (t < n_w1_tiles) {
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            float4* wp = reinterpret_cast<float4*>(W1t + (4 * tk1 + kk) * H + 4 * tj1);
-                            const float4 w4 = *wp;
-                            *wp = make_float4(adam_update(w4.x, g_w1[n][0][kk] * clip_coef, m_w1[n][0][kk], v_w1[n][0][kk], ac),
-                                              adam_update(w4.y, g_w1[n][1][kk] * clip_coef, m_w1[n][1][kk], v_w1[n][1][kk], ac),
-                                              adam_update(w4.z, g_w1[n][2][kk] * clip_coef, m_w1[n][2][kk], v_w1[n][2][kk], ac),
-                                              adam_update(w4.w, g_w1[n][3][kk] * clip_coef, m_w1[n][3][kk], v_w1[n][3][kk], ac));
-                        }
+                for (int i = 0; i < NT1; ++i) {
+                    if (w1_k(i) < KP) {
+                        float2* pa = reinterpret_cast<float2*>(W1 + oj * LDX + w1_k(i));
+                        float2* pb = reinterpret_cast<float2*>(W1 + (oj + 8) * LDX + w1_k(i));
+                        const float2 wa = *pa, wb = *pb;
+                        *pa = make_float2(adam_update(wa.x, g_w1[i][0] * clip_coef, m_w1[i][0], v_w1[i][0], ac),
+                                          adam_update(wa.y, g_w1[i][1] * clip_coef, m_w1[i][1], v_w1[i][1], ac));
+                        *pb = make_float2(adam_update(wb.x, g_w1[i][2] * clip_coef, m_w1[i][2], v_w1[i][2], ac),
+                                          adam_update(wb.y, g_w1[i][3] * clip_coef, m_w1[i][3], v_w1[i][3], ac));
                     }
                 }
                 if (hd < AOUT) {
@@ -918,27 +851,22 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
     }
 #undef ICRL_MARK
 
-    // ---- write back parameters and moments
+    // ---- write back parameters and moments (owner threads)
     if (working) {
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj)
+        for (int nt = 0; nt < NTW2; ++nt)
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                const int j = 4 * tj2 + jj, k = 4 * tk2 + kk, f = flat_w2(j, k);
-                if (f >= 0) { a.params[f] = W2[j * H + k]; a.adam_m[f] = m_w2[jj][kk]; a.adam_v[f] = v_w2[jj][kk]; }
+            for (int c = 0; c < 4; ++c) {
+                const int j = frag_j(c), k = w2_k(nt) + frag_dk(c), f = flat_w2(j, k);
+                if (f >= 0) { a.params[f] = W2[j * LDH + k]; a.adam_m[f] = m_w2[nt][c]; a.adam_v[f] = v_w2[nt][c]; }
             }
 #pragma unroll
-        for (int n = 0; n < NT1; ++n) {
-            const int t = tid + NTH * n, tk1 = t >> 4, tj1 = t & 15;
+        for (int i = 0; i < NT1; ++i)
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const int j = 4 * tj1 + jj, k = 4 * tk1 + kk;
-                    const int f = (t < n_w1_tiles) ? flat_w1(j, k) : -1;
-                    if (f >= 0) { a.params[f] = W1t[k * H + j]; a.adam_m[f] = m_w1[n][jj][kk]; a.adam_v[f] = v_w1[n][jj][kk]; }
-                }
-        }
+            for (int c = 0; c < 4; ++c) {
+                const int j = frag_j(c), k = w1_k(i) + frag_dk(c), f = flat_w1(j, k);
+                if (f >= 0) { a.params[f] = W1[j * LDX + k]; a.adam_m[f] = m_w1[i][c]; a.adam_v[f] = v_w1[i][c]; }
+            }
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             const int f = flat_hw(hd, 4 * hk4 + kk);
@@ -959,129 +887,7 @@ __global__ void __launch_bounds__(NTH, 1) ppo_train_kernel(const __grid_constant
     cluster_sync_all();   // nobody exits while a peer may still address its shared memory
 }
 
-
-// ---------------------------------------------------------------- policy forward (rollout / evaluation side)
-// grid = (row chunks, 3 trunks).  Each CTA keeps its trunk in shared memory and walks 64-row chunks.
-__global__ void __launch_bounds__(NTH) policy_forward_kernel(const __grid_constant__ PpoArgs a, const float* __restrict__ obs,
-                                                             long long n, float* __restrict__ head,
-                                                             float* __restrict__ values, float* __restrict__ cost_values) {
-    extern __shared__ __align__(16) float sm[];
-    const PpoSmem L = ppo_smem_layout(a.DP);
-    const int tid = threadIdx.x, trunk = blockIdx.y, D = a.D, DP = a.DP;
-    const int AOUT = trunk == 0 ? a.A : 1;
-    float* W1t = sm + L.w1t; float* W2t = sm + L.w2t; float* B1 = sm + L.b1; float* B2 = sm + L.b2;
-    float* HW = sm + L.hw; float* HB = sm + L.hb; float* X = sm + L.x; float* H1 = sm + L.h1; float* H2 = sm + L.h2;
-    for (int i = tid; i < DP * H; i += NTH) {
-        const int k = i / H, j = i - k * H;
-        W1t[i] = (k < D && j < a.h0) ? a.params[a.off_w1[trunk] + j * D + k] : 0.f;
-    }
-    for (int i = tid; i < H * H; i += NTH) {
-        const int k = i / H, j = i - k * H;
-        W2t[i] = (k < a.h0 && j < a.h1) ? a.params[a.off_w2[trunk] + j * a.h0 + k] : 0.f;
-    }
-    for (int i = tid; i < AMAX * WA_LD; i += NTH) {
-        const int d = i / WA_LD, k = i - d * WA_LD;
-        HW[i] = (d < AOUT && k < a.h1) ? a.params[a.off_hw[trunk] + d * a.h1 + k] : 0.f;
-    }
-    if (tid < H) {
-        B1[tid] = tid < a.h0 ? a.params[a.off_b1[trunk] + tid] : 0.f;
-        B2[tid] = tid < a.h1 ? a.params[a.off_b2[trunk] + tid] : 0.f;
-    }
-    if (tid < AMAX) HB[tid] = tid < AOUT ? a.params[a.off_hb[trunk] + tid] : 0.f;
-    const int ty = tid >> 4, tx = tid & 15, hr = tid >> 2, hq = tid & 3;
-    const long long n_chunks = (n + RB - 1) / RB;
-    for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-        const long long row0 = c * RB;
-        const int rows = (int)min((long long)RB, n - row0);
-        __syncthreads();
-        for (int i = tid; i < RB * DP; i += NTH) {
-            const int r = i / DP, k = i - r * DP;
-            X[i] = (r < rows && k < D) ? obs[(row0 + r) * D + k] : 0.f;
-        }
-        __syncthreads();
-        float acc[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = B1[4 * tx + j];
-        gemm_tile_4x4<0>(acc, X, DP, W1t, DP, ty, tx);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<float4*>(H1 + (4 * ty + i) * H + 4 * tx) =
-                make_float4(tanhf(acc[i][0]), tanhf(acc[i][1]), tanhf(acc[i][2]), tanhf(acc[i][3]));
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = B2[4 * tx + j];
-        gemm_tile_4x4<H>(acc, H1, H, W2t, H, ty, tx);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<float4*>(H2 + (4 * ty + i) * H + 4 * tx) =
-                make_float4(tanhf(acc[i][0]), tanhf(acc[i][1]), tanhf(acc[i][2]), tanhf(acc[i][3]));
-        __syncthreads();
-        for (int u = 0; u < 4; ++u) {
-            const int d = hq + 4 * u;
-            if (d < AOUT && hr < rows) {
-                float o = HB[d];
-                const float4* hrow = reinterpret_cast<const float4*>(H2 + hr * H);
-                const float4* wrow = reinterpret_cast<const float4*>(HW + d * WA_LD);
-#pragma unroll
-                for (int k = 0; k < H / 4; ++k) {
-                    const float4 h = hrow[k], w = wrow[k];
-                    o = fmaf(h.x, w.x, o); o = fmaf(h.y, w.y, o); o = fmaf(h.z, w.z, o); o = fmaf(h.w, w.w, o);
-                }
-                if (trunk == 0) head[(row0 + hr) * a.A + d] = o;
-                else if (trunk == 1) values[row0 + hr] = o;
-                else cost_values[row0 + hr] = o;
-            }
-        }
-    }
-}
-
 // ---------------------------------------------------------------- host side
-static int fill_offsets(PpoArgs& a) {
-    int o = 0;
-    a.off_logstd = a.is_discrete ? -1 : 0;
-    if (!a.is_discrete) o += a.A;
-    for (int t = 0; t < 3; ++t) {
-        a.off_w1[t] = o; o += a.h0 * a.D;
-        a.off_b1[t] = o; o += a.h0;
-        a.off_w2[t] = o; o += a.h1 * a.h0;
-        a.off_b2[t] = o; o += a.h1;
-    }
-    const int outs[3] = {a.A, 1, 1};
-    for (int t = 0; t < 3; ++t) {
-        a.off_hw[t] = o; o += outs[t] * a.h1;
-        a.off_hb[t] = o; o += outs[t];
-    }
-    return o;
-}
-
-static int make_args(const icrl_ppo_cfg* c, PpoArgs& a) {
-    ICRL_CHECK_ARG(c != nullptr, "ppo cfg is NULL");
-    ICRL_CHECK_ARG(c->obs_dim >= 1, "obs_dim must be >= 1");
-    ICRL_CHECK_ARG(c->act_dim >= 1 && c->act_dim <= AMAX, "act_dim %d out of range (1..%d)", c->act_dim, AMAX);
-    ICRL_CHECK_ARG(c->hidden[0] >= 1 && c->hidden[0] <= H && c->hidden[1] >= 1 && c->hidden[1] <= H,
-                   "policy hidden sizes (%d, %d) must be in 1..%d (two hidden layers per trunk)", c->hidden[0],
-                   c->hidden[1], H);
-    a.D = c->obs_dim; a.DP = (c->obs_dim + 3) / 4 * 4; a.A = c->act_dim; a.is_discrete = c->is_discrete;
-    a.h0 = c->hidden[0]; a.h1 = c->hidden[1];
-    a.T = c->T; a.E = c->E; a.N = c->T * c->E;
-    a.B = c->batch_size > 0 ? c->batch_size : a.N;
-    if (a.B > a.N && a.N > 0) a.B = a.N;
-    a.n_epochs = c->n_epochs;
-    a.steps_per_epoch = a.N > 0 ? (a.N + a.B - 1) / a.B : 0;
-    a.max_steps = c->max_steps;
-    a.has_target_kl = c->has_target_kl; a.has_clip_vf_r = c->has_clip_vf_reward; a.has_clip_vf_c = c->has_clip_vf_cost;
-    a.clip_range = c->clip_range; a.clip_vf_r = c->clip_range_reward_vf; a.clip_vf_c = c->clip_range_cost_vf;
-    a.ent_coef = c->ent_coef; a.vf_coef_r = c->reward_vf_coef; a.vf_coef_c = c->cost_vf_coef;
-    a.max_grad_norm = c->max_grad_norm; a.nu = c->nu; a.target_kl = c->target_kl;
-    a.lr = c->lr; a.beta1 = c->adam_beta1; a.beta2 = c->adam_beta2; a.adam_eps = c->adam_eps;
-    fill_offsets(a);
-    return 0;
-}
-
 template <int NT1>
 static int launch_ppo(const PpoArgs& a, cudaStream_t st) {
     auto kern = ppo_train_kernel<NT1>;
@@ -1096,7 +902,7 @@ static int launch_ppo(const PpoArgs& a, cudaStream_t st) {
     for (int cluster = 3; cluster <= 4; ++cluster) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(cluster);
-        cfg.blockDim = dim3(NTH);
+        cfg.blockDim = dim3(NTT);
         cfg.dynamicSmemBytes = L.total_bytes;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
@@ -1124,14 +930,14 @@ extern "C" {
 
 int64_t icrl_ppo_param_count(const icrl_ppo_cfg* cfg) {
     icrl::PpoArgs a = {};
-    if (icrl::make_args(cfg, a)) return -1;
-    return icrl::fill_offsets(a);
+    if (icrl::ppo_make_args(cfg, a)) return -1;
+    return icrl::ppo_fill_offsets(a);
 }
 
 int icrl_ppo_train(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* params, float* adam_m, float* adam_v,
                    int64_t adam_step_before, float* step_stats, int32_t* result, void* stream) {
     icrl::PpoArgs a = {};
-    int rc = icrl::make_args(cfg, a);
+    int rc = icrl::ppo_make_args(cfg, a);
     if (rc) return rc;
     ICRL_CHECK_ARG(data && params && adam_m && adam_v && step_stats && result, "NULL pointer passed to icrl_ppo_train");
     ICRL_CHECK_ARG(a.N > 0 && a.n_epochs > 0, "empty rollout buffer or n_epochs <= 0");
@@ -1149,6 +955,7 @@ int icrl_ppo_train(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* pa
     a.nu_dev = data->nu_device;
     a.params = params; a.adam_m = adam_m; a.adam_v = adam_v; a.stats = step_stats; a.result = result;
     a.step_before = adam_step_before;
+    cudaStream_t st = (cudaStream_t)stream;
     {
         const int total_steps = a.n_epochs * a.steps_per_epoch;
         const long long n_rows = (long long)a.n_epochs * a.N, n_alloc = n_rows + icrl::RB;
@@ -1161,11 +968,10 @@ int icrl_ppo_train(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* pa
         if ((rc = icrl::device_scratch(icrl::SLOT_PPO3, (size_t)n_alloc * 8 * 4, &ss))) return rc;
         const long long blocks = (n_alloc + 7) / 8;
         const int grid = (int)(blocks < 8LL * icrl::sm_count() ? blocks : 8LL * icrl::sm_count());
-        icrl::ppo_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, (float*)xs, (float*)as, (float*)ss, n_rows, n_alloc);
+        icrl::ppo_gather_kernel<<<grid, 256, 0, st>>>(a, (float*)xs, (float*)as, (float*)ss, n_rows, n_alloc);
         ICRL_LAUNCH_CHECK();
-        icrl::ppo_stats_kernel<<<total_steps, 128, 0, (cudaStream_t)stream>>>((const float*)ss, (float*)advstats, a.N, a.B,
-                                                                             a.steps_per_epoch, a.beta1, a.beta2, a.lr,
-                                                                             a.step_before);
+        icrl::ppo_stats_kernel<<<total_steps, 128, 0, st>>>((const float*)ss, (float*)advstats, a.N, a.B, a.steps_per_epoch,
+                                                            a.beta1, a.beta2, a.lr, a.step_before);
         ICRL_LAUNCH_CHECK();
         a.xs = (const float*)xs; a.as = (const float*)as; a.ss = (const float*)ss;
         a.advstats = (const float*)advstats;
@@ -1174,19 +980,20 @@ int icrl_ppo_train(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* pa
     const bool want_timing = getenv("ICRL_PPO_TIMING") != nullptr;
     if (want_timing && !timing_dev) cudaMalloc(&timing_dev, 48 * sizeof(unsigned long long));
     a.timing = want_timing ? timing_dev : nullptr;
-    const int n_tiles = 16 * (a.DP / 4);
-    const int nt1 = (n_tiles + icrl::NTH - 1) / icrl::NTH;
-    switch (nt1) {
-        case 1: rc = icrl::launch_ppo<1>(a, (cudaStream_t)stream); break;
-        case 2: rc = icrl::launch_ppo<2>(a, (cudaStream_t)stream); break;
-        case 3: rc = icrl::launch_ppo<3>(a, (cudaStream_t)stream); break;
-        default:
-            icrl::set_error("obs_dim %d too large for the PPO kernel (max 192)", a.D);
-            return ICRL_EUNSUPPORTED;
+    const int n_tiles = a.KP / 8;                 // n-tiles of dW1; each warp owns every second one
+    const int nt1 = (n_tiles + 1) / 2;
+    if (nt1 <= 1) rc = icrl::launch_ppo<1>(a, st);
+    else if (nt1 <= 2) rc = icrl::launch_ppo<2>(a, st);
+    else if (nt1 <= 4) rc = icrl::launch_ppo<4>(a, st);
+    else if (nt1 <= 8) rc = icrl::launch_ppo<8>(a, st);
+    else if (nt1 <= 12) rc = icrl::launch_ppo<12>(a, st);
+    else {
+        icrl::set_error("obs_dim %d too large for the PPO kernel (max 192)", a.D);
+        return ICRL_EUNSUPPORTED;
     }
     if (rc == 0 && want_timing) {   // profiling aid: per-phase cycles of thread 0 of each trunk CTA (synchronises!)
         unsigned long long h[48];
-        cudaStreamSynchronize((cudaStream_t)stream);
+        cudaStreamSynchronize(st);
         cudaMemcpy(h, timing_dev, sizeof(h), cudaMemcpyDeviceToHost);
         const char* names[11] = {"wait+sync", "prefetch", "L1", "L2", "head", "headgrad+dH2", "dW2+dH1", "dW1", "reduce+stats",
                                  "xchg+cluster", "adam"};
@@ -1199,27 +1006,6 @@ int icrl_ppo_train(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* pa
         }
     }
     return rc;
-}
-
-int icrl_policy_forward(const icrl_ppo_cfg* cfg, const float* params, const float* obs, int64_t n, float* head,
-                        float* values, float* cost_values, void* stream) {
-    icrl::PpoArgs a = {};
-    icrl_ppo_cfg c = *cfg;
-    if (c.T <= 0) c.T = 1;
-    if (c.E <= 0) c.E = 1;
-    int rc = icrl::make_args(&c, a);
-    if (rc) return rc;
-    if (n == 0) return 0;
-    ICRL_CHECK_ARG(params && obs && head && values && cost_values && n > 0, "NULL pointer passed to icrl_policy_forward");
-    a.params = const_cast<float*>(params);
-    const icrl::PpoSmem L = icrl::ppo_smem_layout(a.DP);
-    ICRL_CUDA(cudaFuncSetAttribute(icrl::policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes));
-    const int64_t chunks = (n + icrl::RB - 1) / icrl::RB;
-    const int gx = (int)(chunks < icrl::sm_count() ? chunks : icrl::sm_count());
-    icrl::policy_forward_kernel<<<dim3(gx, 3), icrl::NTH, L.total_bytes, (cudaStream_t)stream>>>(a, obs, n, head, values,
-                                                                                                cost_values);
-    ICRL_LAUNCH_CHECK();
-    return 0;
 }
 
 }  // extern "C"
