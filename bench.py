@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=300, help="K4 optimiser steps in the CPU sample")
+    ap.add_argument("--replicas", action="store_true", help="N>1: independent learners instead of data-parallel all-reduce")
     return ap.parse_args()
 
 
@@ -377,7 +378,12 @@ def main():
     th.cuda.set_device(local)
     from icrl_b200 import _lib
     peak, peak_src = measured_peaks()
-    learner = DeviceLearner(w, seed=rank, device=th.device("cuda", local))
+    comm = None
+    if world > 1 and not args.replicas:
+        from icrl_b200.distributed import PpoComm
+        comm = PpoComm()
+    # data parallel: every rank owns n_envs environments (its own rollouts, seed = rank); networks and K2 batches replicated
+    learner = DeviceLearner(w, seed=rank, device=th.device("cuda", local), comm=comm, param_seed=0)
     flush = th.zeros(64 * 1024 * 1024, device="cuda")      # 256 MB
     for _ in range(args.warmup):
         learner.run()
@@ -405,7 +411,7 @@ def main():
             hl.run()
         th.cuda.synchronize()
         t_e2e = max_over_ranks(time.perf_counter() - t0, world) / args.steps
-        e2e = {"value": total_tr / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(hl.h2d), "d2h_bytes_per_step": int(hl.d2h),
+        e2e = {"value": total_tr / t_e2e, "unit": UNIT, "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas", "h2d_bytes_per_step": int(hl.h2d), "d2h_bytes_per_step": int(hl.d2h),
                "ms_per_step": t_e2e * 1e3, "path": "ConstraintNet.cost_function / RolloutBufferWithCost.compute_returns_and_advantage"
                " / PPOLagrangian.train / ConstraintNet.train with numpy buffers (pinned staging + async H2D, D2H of costs, "
                "advantages, per-step stats, metrics)"}
@@ -430,9 +436,13 @@ def main():
                        "rollouts": w.rollouts, "n_steps": w.n_steps, "n_envs_per_gpu": w.n_envs, "batch_size": w.batch_size,
                        "n_epochs": w.n_epochs, "backward_iters": w.backward_iters, "early_stop": "disabled (fixed work)",
                        "l2": "flushed between timed steps (256 MB write, outside the timed region)",
-                       "parallelism": "1 GPU" if world == 1 else f"{world} independent learner replicas, one per GPU (no data-path "
-                                      "collective; see DESIGN.md multi-GPU)"},
+                       "parallelism": "1 GPU" if world == 1 else (
+                           f"{world} independent learner replicas" if args.replicas else
+                           f"dp{world}: env-sharded rollouts (K1/K3 local), K4 gradients all-reduced inside the persistent kernel "
+                           f"over NVLink peer memory every optimiser step (global batch {w.batch_size * world}), K2 replicated")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "kernels": fam, "cpu_baseline": cpu}))
+    if comm is not None:
+        comm.close()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

@@ -61,6 +61,14 @@ class PpoData(C.Structure):
         "old_cost_values", "cost_advantages", "cost_returns", "perm", "nu_device")]
 
 
+class PpoDist(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("recv", c_void * 8), ("flags", c_void * 8),
+                ("flag_base", C.c_uint32), ("advsums", c_void)]
+
+
+PPO_RECV_BYTES = 2 * 8 * 3 * 72 * 256 * 4
+PPO_FLAG_BYTES = 2 * 8 * 4 * 4
+
 # name -> (restype, argtypes); every symbol include/icrl_b200.h declares (checked by tests/test_abi.py)
 SIGNATURES = {
     "icrl_abi_version": (C.c_int, []),
@@ -79,6 +87,13 @@ SIGNATURES = {
     "icrl_ppo_param_count": (C.c_int64, [C.POINTER(PpoCfg)]),
     "icrl_ppo_train": (C.c_int, [C.POINTER(PpoCfg), C.POINTER(PpoData), c_void, c_void, c_void, C.c_int64, c_void,
                                  c_void, c_void]),
+    "icrl_ppo_train_dist": (C.c_int, [C.POINTER(PpoCfg), C.POINTER(PpoData), c_void, c_void, c_void, C.c_int64, c_void,
+                                      c_void, C.POINTER(PpoDist), c_void]),
+    "icrl_ppo_local_advsums": (C.c_int, [C.POINTER(PpoCfg), C.POINTER(PpoData), c_void, c_void]),
+    "icrl_comm_alloc": (C.c_int, [C.c_int64, C.POINTER(c_void), C.c_char_p]),
+    "icrl_comm_open": (C.c_int, [C.c_char_p, C.POINTER(c_void)]),
+    "icrl_comm_close": (C.c_int, [c_void]),
+    "icrl_comm_free": (C.c_int, [c_void]),
     "icrl_policy_forward": (C.c_int, [C.POINTER(PpoCfg), c_void, c_void, C.c_int64, c_void, c_void, c_void, c_void]),
     "icrl_dual_update": (C.c_int, [c_void, c_void, C.c_int64, C.c_double, C.c_double, C.c_int64, C.c_double, c_void]),
 }

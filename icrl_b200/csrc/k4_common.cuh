@@ -44,7 +44,14 @@ struct PpoArgs {
     float *params, *adam_m, *adam_v, *stats;
     int* result;
     unsigned long long* timing;   // optional [3 roles][16 phases] cycle accumulators (profiling aid)
+    // data-parallel mode (world > 1): peer receive buffers / flags (CUDA IPC mapped), see include/icrl_b200.h
+    int rank, world;
+    float* recv[ICRL_PPO_MAX_RANKS];
+    unsigned int* flags[ICRL_PPO_MAX_RANKS];
+    unsigned int flag_base;
+    const double* advsums;        // all-reduced per-step sums (sum adv_r, sum adv_r^2, sum adv_c, count) or NULL
 };
+constexpr int DIST_SLOTS = 72;    // floats per thread in a receive-buffer slab
 
 inline int ppo_fill_offsets(PpoArgs& a) {
     int o = 0;

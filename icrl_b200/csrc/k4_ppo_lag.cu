@@ -184,9 +184,25 @@ __global__ void __launch_bounds__(256) ppo_gather_kernel(const __grid_constant__
 // corrections.  They depend only on data and the step number, never on parameters.
 __global__ void __launch_bounds__(128) ppo_stats_kernel(const float* __restrict__ ss, float* __restrict__ advstats, int N,
                                                         int B, int spe, double beta1, double beta2, double lr,
-                                                        long long step_before) {
+                                                        long long step_before, const double* __restrict__ advsums) {
     __shared__ double red[2][4];
     const int step = blockIdx.x, epoch = step / spe, mb = step - epoch * spe;
+    if (advsums != nullptr) {
+        // data-parallel: statistics of the GLOBAL minibatch from the all-reduced sums (float64, so the one-pass
+        // variance formula is safe)
+        if (threadIdx.x == 0) {
+            const double sx = advsums[step * 4 + 0], sxx = advsums[step * 4 + 1], sc = advsums[step * 4 + 2],
+                         n = advsums[step * 4 + 3];
+            const double mean = sx / n;
+            advstats[step * 8 + 0] = (float)mean;
+            advstats[step * 8 + 1] = (float)sqrt(fmax(sxx - sx * mean, 0.0) / (n - 1.0));
+            advstats[step * 8 + 2] = (float)(sc / n);
+            const double t = (double)(step_before + step + 1);
+            advstats[step * 8 + 3] = (float)(1.0 / sqrt(1.0 - pow(beta2, t)));
+            advstats[step * 8 + 4] = (float)(-(lr / (1.0 - pow(beta1, t))));
+        }
+        return;
+    }
     const int Bn = min(B, N - mb * B);
     const size_t base = (size_t)epoch * N + (size_t)mb * B;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -219,6 +235,41 @@ __global__ void __launch_bounds__(128) ppo_stats_kernel(const float* __restrict_
         advstats[step * 8 + 3] = (float)(1.0 / sqrt(1.0 - pow(beta2, t)));
         advstats[step * 8 + 4] = (float)(-(lr / (1.0 - pow(beta1, t))));
     }
+}
+
+// Local partial sums of the per-step advantage statistics (data-parallel mode): sum adv_r, sum adv_r^2, sum adv_c, count.
+__global__ void __launch_bounds__(128) ppo_local_advsums_kernel(const int* __restrict__ perm, const float* __restrict__ adv_r,
+                                                                const float* __restrict__ adv_c, int T, int E, int N, int B,
+                                                                int spe, double* __restrict__ out) {
+    __shared__ double red[3][4];
+    const int step = blockIdx.x, epoch = step / spe, mb = step - epoch * spe;
+    const int Bn = min(B, N - mb * B);
+    const size_t base = (size_t)epoch * N + (size_t)mb * B;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double sx = 0.0, sxx = 0.0, sc = 0.0;
+    for (int i = tid; i < Bn; i += blockDim.x) {
+        const int row = perm[base + i], t = row % T, e = row / T, o = t * E + e;
+        const double x = (double)adv_r[o];
+        sx += x; sxx += x * x; sc += (double)adv_c[o];
+    }
+    sx = warp_sum(sx); sxx = warp_sum(sxx); sc = warp_sum(sc);
+    if (lane == 0) { red[0][warp] = sx; red[1][warp] = sxx; red[2][warp] = sc; }
+    __syncthreads();
+    if (tid == 0) {
+        out[step * 4 + 0] = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+        out[step * 4 + 1] = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+        out[step * 4 + 2] = red[2][0] + red[2][1] + red[2][2] + red[2][3];
+        out[step * 4 + 3] = (double)Bn;
+    }
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
 // ---------------------------------------------------------------- the persistent train kernel
@@ -395,7 +446,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
         for (int mb = 0; mb < a.steps_per_epoch && !stop_all; ++mb, ++step) {
             const int parity = step & 1;
             const int Bn = min(a.B, a.N - mb * a.B);
-            const float invB = 1.0f / (float)Bn;
+            const float invB = 1.0f / (float)(Bn * a.world);   // data-parallel: every rank holds Bn rows of the global minibatch
 
             // gradient accumulators (registers, mma C-fragment layout)
             float g_w2[NTW2][4], g_w1[NT1][4], g_hw[4], g_s = 0.f;
@@ -713,49 +764,125 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                 }  // chunks
             }      // working
 
-            // ---- one merged block reduction: loss partial sums + local sum of squared gradients
-            float ss = 0.f;
-            if (working) {
+            // ---- block reductions: the five loss partial sums and the sum of squared gradients.  Single GPU: one merged
+            // reduction.  Data parallel: the loss sums first (the pi CTA's KL partial travels with the gradients), then
+            // the in-kernel all-reduce over NVLink peer memory, then the norm of the REDUCED gradient.
+            auto block_reduce = [&](float (&r)[6]) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) ss = fmaf(g_hw[i], g_hw[i], ss);
+                for (int i = 0; i < 6; ++i) r[i] = warp_sum(r[i]);
+                __syncthreads();      // scratch may still be read from the previous use
+                if (lane == 0) {
 #pragma unroll
-                for (int i = 0; i < NTW2; ++i)
+                    for (int i = 0; i < 6; ++i) scratch[warp * 8 + i] = r[i];
+                }
+                __syncthreads();
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) ss = fmaf(g_w2[i][c], g_w2[i][c], ss);
+                for (int i = 0; i < 6; ++i) {
+                    float tsum = 0.f;
 #pragma unroll
-                for (int i = 0; i < NT1; ++i)
+                    for (int wv = 0; wv < NWT; ++wv) tsum += scratch[wv * 8 + i];
+                    r[i] = tsum;
+                }
+            };
+            auto local_sumsq = [&]() {
+                float q2 = 0.f;
+                if (working) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) ss = fmaf(g_w1[i][c], g_w1[i][c], ss);
-                ss = fmaf(g_s, g_s, ss);
+                    for (int i = 0; i < 4; ++i) q2 = fmaf(g_hw[i], g_hw[i], q2);
+#pragma unroll
+                    for (int i = 0; i < NTW2; ++i)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) q2 = fmaf(g_w2[i][c], g_w2[i][c], q2);
+#pragma unroll
+                    for (int i = 0; i < NT1; ++i)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) q2 = fmaf(g_w1[i][c], g_w1[i][c], q2);
+                    q2 = fmaf(g_s, g_s, q2);
+                }
+                return q2;
+            };
+            float red[6] = {s_a, s_b, s_c, s_d, s_e, 0.f};
+            float kl_global = 0.f;
+            if (a.world == 1) {
+                red[5] = local_sumsq();
+                block_reduce(red);
+                kl_global = red[3] * invB;
+            } else {
+                block_reduce(red);
+                if (working) {
+                    // (1) push this rank's gradient fragments (+ the KL partial) into every rank's receive buffer
+                    const float kl_part = (role == 0 && tid == 0) ? red[3] * invB : 0.f;
+                    const size_t slab = ((size_t)(parity * ICRL_PPO_MAX_RANKS + a.rank) * 3 + role) * DIST_SLOTS * NTT + tid;
+                    for (int p = 0; p < a.world; ++p) {
+                        float* dst = a.recv[p] + slab;
+                        int sl = 0;
+#pragma unroll
+                        for (int i = 0; i < NTW2; ++i)
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) dst[(sl++) * NTT] = g_w2[i][c];
+#pragma unroll
+                        for (int i = 0; i < NT1; ++i)
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) dst[(sl++) * NTT] = g_w1[i][c];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) dst[(sl++) * NTT] = g_hw[i];
+                        dst[(sl++) * NTT] = g_s;
+                        dst[(sl++) * NTT] = kl_part;
+                    }
+                    __threadfence_system();
+                    __syncthreads();
+                    const unsigned int want = a.flag_base + (unsigned int)step + 1u;
+                    const int fidx = parity * ICRL_PPO_MAX_RANKS * 4;
+                    if (tid < a.world) st_release_sys(a.flags[tid] + fidx + a.rank * 4 + role, want);
+                    // (2) wait for every rank's flag for this step (spin with a ~2 s budget so a dead peer cannot hang the GPU)
+                    if (tid < a.world) {
+                        const unsigned int* f = a.flags[a.rank] + fidx + tid * 4 + role;
+                        const long long t0 = clock64();
+                        while ((int)(ld_acquire_sys(f) - want) < 0) {
+                            if (clock64() - t0 > 4000000000LL) { XCH[15] = 1.f; break; }
+                        }
+                    }
+                    __syncthreads();
+                    // (3) add the partials in rank order (identical on every rank -> bit-identical replicated updates)
+                    const float* src0 = a.recv[a.rank] + ((size_t)(parity * ICRL_PPO_MAX_RANKS) * 3 + role) * DIST_SLOTS * NTT + tid;
+                    const size_t rstride = (size_t)3 * DIST_SLOTS * NTT;
+                    auto gsum = [&](int sl) {
+                        float v = 0.f;
+                        for (int r = 0; r < a.world; ++r) v += __ldcg(src0 + r * rstride + (size_t)sl * NTT);
+                        return v;
+                    };
+                    int sl = 0;
+#pragma unroll
+                    for (int i = 0; i < NTW2; ++i)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) g_w2[i][c] = gsum(sl++);
+#pragma unroll
+                    for (int i = 0; i < NT1; ++i)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) g_w1[i][c] = gsum(sl++);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) g_hw[i] = gsum(sl++);
+                    g_s = gsum(sl++);
+                    if (role == 0 && tid == 0) scratch[127] = gsum(sl);    // global KL of this step
+                }
+                float r2[6] = {0.f, 0.f, 0.f, 0.f, 0.f, local_sumsq()};
+                block_reduce(r2);
+                red[5] = r2[5];
+                kl_global = scratch[127];
             }
-            float red[6] = {s_a, s_b, s_c, s_d, s_e, ss};
-#pragma unroll
-            for (int i = 0; i < 6; ++i) red[i] = warp_sum(red[i]);
-            if (lane == 0) {
-#pragma unroll
-                for (int i = 0; i < 6; ++i) scratch[warp * 8 + i] = red[i];
-            }
-            __syncthreads();
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                float tsum = 0.f;
-#pragma unroll
-                for (int wv = 0; wv < NWT; ++wv) tsum += scratch[wv * 8 + i];
-                red[i] = tsum;
-            }
-            ss = red[5];
+            const float ss = red[5];
             const size_t so = (size_t)step * ICRL_PPO_STATS_PER_STEP;
             float kl_step = 0.f;
             if (role == 0) {
                 float pl = -(red[0] * invB);
                 pl = pl + nu * (red[1] * invB);
                 pl = pl / (1.f + nu);
-                kl_step = red[3] * invB;
+                kl_step = kl_global;
                 if (tid == 0) {
                     a.stats[so + 0] = pl;
                     a.stats[so + 1] = red[2] * invB;
                     a.stats[so + 4] = -(red[4] * invB);
-                    a.stats[so + 5] = kl_step;
+                    a.stats[so + 5] = red[3] * invB;
                 }
             } else if (working) {
                 if (tid == 0) a.stats[so + (role == 1 ? 2 : 3)] = red[0] * invB;
@@ -881,7 +1008,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
     if (role == 0 && tid == 0) {
         a.result[0] = early_stop_epoch;
         a.result[1] = step;
-        a.result[2] = 0;
+        a.result[2] = (XCH[15] != 0.f) ? 1 : 0;   // a peer timed out in data-parallel mode
         a.result[3] = 0;
     }
     cluster_sync_all();   // nobody exits while a peer may still address its shared memory
@@ -934,11 +1061,22 @@ int64_t icrl_ppo_param_count(const icrl_ppo_cfg* cfg) {
     return icrl::ppo_fill_offsets(a);
 }
 
-int icrl_ppo_train(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* params, float* adam_m, float* adam_v,
-                   int64_t adam_step_before, float* step_stats, int32_t* result, void* stream) {
+static int ppo_train_impl(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* params, float* adam_m, float* adam_v,
+                          int64_t adam_step_before, float* step_stats, int32_t* result, const icrl_ppo_dist* dist,
+                          void* stream) {
     icrl::PpoArgs a = {};
     int rc = icrl::ppo_make_args(cfg, a);
     if (rc) return rc;
+    if (dist) {
+        ICRL_CHECK_ARG(dist->world >= 1 && dist->world <= ICRL_PPO_MAX_RANKS && dist->rank >= 0 && dist->rank < dist->world,
+                       "bad rank/world (%d/%d)", dist->rank, dist->world);
+        a.rank = dist->rank; a.world = dist->world; a.flag_base = dist->flag_base; a.advsums = dist->advsums;
+        for (int r = 0; r < dist->world; ++r) {
+            ICRL_CHECK_ARG(dist->world == 1 || (dist->recv[r] && dist->flags[r]), "peer buffer %d is NULL", r);
+            a.recv[r] = dist->recv[r]; a.flags[r] = dist->flags[r];
+        }
+        ICRL_CHECK_ARG(dist->world == 1 || dist->advsums, "data-parallel mode needs the all-reduced advsums table");
+    }
     ICRL_CHECK_ARG(data && params && adam_m && adam_v && step_stats && result, "NULL pointer passed to icrl_ppo_train");
     ICRL_CHECK_ARG(a.N > 0 && a.n_epochs > 0, "empty rollout buffer or n_epochs <= 0");
     ICRL_CHECK_ARG(data->observations && data->actions && data->old_log_prob && data->reward_advantages &&
@@ -955,6 +1093,7 @@ int icrl_ppo_train(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* pa
     a.nu_dev = data->nu_device;
     a.params = params; a.adam_m = adam_m; a.adam_v = adam_v; a.stats = step_stats; a.result = result;
     a.step_before = adam_step_before;
+    if (a.world < 1) { a.world = 1; a.rank = 0; }
     cudaStream_t st = (cudaStream_t)stream;
     {
         const int total_steps = a.n_epochs * a.steps_per_epoch;
@@ -971,7 +1110,7 @@ int icrl_ppo_train(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* pa
         icrl::ppo_gather_kernel<<<grid, 256, 0, st>>>(a, (float*)xs, (float*)as, (float*)ss, n_rows, n_alloc);
         ICRL_LAUNCH_CHECK();
         icrl::ppo_stats_kernel<<<total_steps, 128, 0, st>>>((const float*)ss, (float*)advstats, a.N, a.B, a.steps_per_epoch,
-                                                            a.beta1, a.beta2, a.lr, a.step_before);
+                                                            a.beta1, a.beta2, a.lr, a.step_before, a.advsums);
         ICRL_LAUNCH_CHECK();
         a.xs = (const float*)xs; a.as = (const float*)as; a.ss = (const float*)ss;
         a.advstats = (const float*)advstats;
@@ -1006,6 +1145,30 @@ int icrl_ppo_train(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* pa
         }
     }
     return rc;
+}
+
+int icrl_ppo_train(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* params, float* adam_m, float* adam_v,
+                   int64_t adam_step_before, float* step_stats, int32_t* result, void* stream) {
+    return ppo_train_impl(cfg, data, params, adam_m, adam_v, adam_step_before, step_stats, result, nullptr, stream);
+}
+
+int icrl_ppo_train_dist(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* params, float* adam_m, float* adam_v,
+                        int64_t adam_step_before, float* step_stats, int32_t* result, const icrl_ppo_dist* dist,
+                        void* stream) {
+    ICRL_CHECK_ARG(dist != nullptr, "dist is NULL");
+    return ppo_train_impl(cfg, data, params, adam_m, adam_v, adam_step_before, step_stats, result, dist, stream);
+}
+
+int icrl_ppo_local_advsums(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, double* advsums_out, void* stream) {
+    icrl::PpoArgs a = {};
+    int rc = icrl::ppo_make_args(cfg, a);
+    if (rc) return rc;
+    ICRL_CHECK_ARG(data && advsums_out && data->perm && data->reward_advantages && data->cost_advantages && a.N > 0,
+                   "NULL pointer passed to icrl_ppo_local_advsums");
+    icrl::ppo_local_advsums_kernel<<<a.n_epochs * a.steps_per_epoch, 128, 0, (cudaStream_t)stream>>>(
+        data->perm, data->reward_advantages, data->cost_advantages, a.T, a.E, a.N, a.B, a.steps_per_epoch, advsums_out);
+    ICRL_LAUNCH_CHECK();
+    return 0;
 }
 
 }  // extern "C"

@@ -118,14 +118,19 @@ def spaces_of(w: Workload):
 class DeviceLearner:
     """Device-resident learner state + data for one workload.  `run()` enqueues one full ICRL learner iteration."""
 
-    def __init__(self, w: Workload, seed: int = 0, device="cuda", n_envs: Optional[int] = None, fixed_work: bool = True):
+    def __init__(self, w: Workload, seed: int = 0, device="cuda", n_envs: Optional[int] = None, fixed_work: bool = True,
+                 comm=None, param_seed: Optional[int] = None):
+        """`comm` (icrl_b200.distributed.PpoComm): data-parallel mode -- this rank's rollouts (seed) differ per rank, the
+        networks and the K2 batches (param_seed) are replicated."""
         self.w, self.dev = w, resolve_device(device)
         self.E = n_envs or w.n_envs
-        th.manual_seed(seed)
+        self.comm = comm
+        param_seed = seed if param_seed is None else param_seed
+        th.manual_seed(param_seed)
         obs_space, act_space = spaces_of(w)
         self.policy = ActorTwoCriticsPolicy(obs_space, act_space, lambda _: w.learning_rate, device=self.dev)
         self.dual = DualVariable(0.0, w.penalty_learning_rate, w.penalty_initial_value, device=self.dev)
-        eo, ea, no, na, lengths = synth_demos(w, seed)
+        eo, ea, no, na, lengths = synth_demos(w, param_seed)
         low = high = None
         if not w.is_discrete:
             low, high = -np.ones(w.act_dim, np.float32), np.ones(w.act_dim, np.float32)
@@ -161,6 +166,9 @@ class DeviceLearner:
             off[1:] = np.cumsum(lengths)
             self.offsets, self.n_episodes = th.from_numpy(off).to(d), len(lengths)
         self.max_steps = 0
+        if comm is not None and comm.world > 1:
+            self.advsums = th.zeros(w.n_epochs * self.steps_per_epoch, 4, dtype=th.float64, device=d)
+            self.cost_mean = th.zeros(1, device=d)
         self.refresh_behaviour()
         self.new_permutations(seed)
 
@@ -219,13 +227,32 @@ class DeviceLearner:
             data.reward_advantages, data.reward_returns = self.adv_r[r].data_ptr(), self.ret_r[r].data_ptr()
             data.cost_advantages, data.cost_returns = self.adv_c[r].data_ptr(), self.ret_c[r].data_ptr()
             data.perm = self.perm[r].data_ptr()
-            _lib.check(L.icrl_ppo_train(C.byref(cfg), C.byref(data), _lib.ptr(pol._params), _lib.ptr(pol._adam_m),
-                                        _lib.ptr(pol._adam_v), pol.optimizer.step_count, _lib.ptr(self.stats[r]),
-                                        _lib.ptr(self.result[r]), st))
+            dp = self.comm is not None and self.comm.world > 1
+            if not dp:
+                _lib.check(L.icrl_ppo_train(C.byref(cfg), C.byref(data), _lib.ptr(pol._params), _lib.ptr(pol._adam_m),
+                                            _lib.ptr(pol._adam_v), pol.optimizer.step_count, _lib.ptr(self.stats[r]),
+                                            _lib.ptr(self.result[r]), st))
+            else:
+                # global-minibatch advantage statistics: local partial sums -> one small NCCL all-reduce
+                _lib.check(L.icrl_ppo_local_advsums(C.byref(cfg), C.byref(data), _lib.ptr(self.advsums), st))
+                self.comm.all_reduce_sum(self.advsums)
+                desc_d = self.comm.descriptor(self.advsums)
+                _lib.check(L.icrl_ppo_train_dist(C.byref(cfg), C.byref(data), _lib.ptr(pol._params), _lib.ptr(pol._adam_m),
+                                                 _lib.ptr(pol._adam_v), pol.optimizer.step_count, _lib.ptr(self.stats[r]),
+                                                 _lib.ptr(self.result[r]), C.byref(desc_d), _lib.current_stream()))
+                self.comm.advance(self.steps_taken_per_rollout())
             pol.optimizer.step_count += self.steps_taken_per_rollout()
-            # dual step on the rollout's (relabelled) costs
-            _lib.check(L.icrl_dual_update(_lib.ptr(self.dual.nu.state), _lib.ptr(self.costs[r]), self.n, 0.0,
-                                          float(w.penalty_learning_rate), self.dual.steps, self.dual.nu.clamp_min(), st))
+            # dual step on the rollout's (relabelled) costs -- over every rank's environments in data-parallel mode
+            if not dp:
+                _lib.check(L.icrl_dual_update(_lib.ptr(self.dual.nu.state), _lib.ptr(self.costs[r]), self.n, 0.0,
+                                              float(w.penalty_learning_rate), self.dual.steps, self.dual.nu.clamp_min(), st))
+            else:
+                self.cost_mean.copy_(self.costs[r].mean().reshape(1))
+                self.comm.all_reduce_sum(self.cost_mean)
+                self.cost_mean /= self.comm.world
+                _lib.check(L.icrl_dual_update(_lib.ptr(self.dual.nu.state), _lib.ptr(self.cost_mean), 1, 0.0,
+                                              float(w.penalty_learning_rate), self.dual.steps, self.dual.nu.clamp_min(),
+                                              _lib.current_stream()))
             self.dual.steps += 1
         if w.backward_iters > 0 and w.nominal_rows > 0:
             self._cn_train_device()

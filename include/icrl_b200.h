@@ -194,6 +194,42 @@ int64_t icrl_ppo_param_count(const icrl_ppo_cfg* cfg);
 int icrl_ppo_train(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* params, float* adam_m, float* adam_v,
                    int64_t adam_step_before, float* step_stats, int32_t* result, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Data-parallel K4 across the GPUs of one node (one process per GPU).  Every rank owns the rollout
+ * of its own environments and runs the same persistent kernel on `batch_size` LOCAL rows per optimiser step; the
+ * gradients of the three trunks are summed across ranks INSIDE the kernel: each CTA stores its gradient fragments
+ * straight into every peer's receive buffer over NVLink (CUDA IPC mapped memory), raises a per-step flag, waits for the
+ * peers' flags and adds the partials in rank order, so all ranks apply bit-identical Adam updates and the replicated
+ * parameters never drift.  The global-minibatch advantage statistics (ppo_lag.py:218-222) are data-only, so the caller
+ * all-reduces one small table up front (icrl_ppo_local_advsums -> NCCL all-reduce -> icrl_ppo_dist.advsums).
+ */
+#define ICRL_PPO_MAX_RANKS 8
+#define ICRL_PPO_RECV_BYTES (2 * ICRL_PPO_MAX_RANKS * 3 * 72 * 256 * 4) /* [parity][src][trunk][slot][thread] float */
+#define ICRL_PPO_FLAG_BYTES (2 * ICRL_PPO_MAX_RANKS * 4 * 4)             /* [parity][src][trunk] uint32 */
+
+int icrl_comm_alloc(int64_t bytes, void** dev_ptr, unsigned char* handle64);   /* zeroed device buffer + its IPC handle */
+int icrl_comm_open(const unsigned char* handle64, void** dev_ptr);              /* map a peer's buffer */
+int icrl_comm_close(void* dev_ptr);
+int icrl_comm_free(void* dev_ptr);
+
+typedef struct icrl_ppo_dist {
+    int32_t rank, world;
+    float* recv[ICRL_PPO_MAX_RANKS];       /* recv[r]: rank r's receive buffer (ICRL_PPO_RECV_BYTES); recv[rank] is local */
+    uint32_t* flags[ICRL_PPO_MAX_RANKS];   /* flags[r]: rank r's flag array (ICRL_PPO_FLAG_BYTES) */
+    uint32_t flag_base;                    /* monotonically growing; every rank advances it by steps+1 after each launch */
+    const double* advsums;                 /* device [n_epochs*steps_per_epoch][4]: all-reduced sum adv_r, sum adv_r^2,
+                                              sum adv_c, row count of every global minibatch */
+} icrl_ppo_dist;
+
+/* local partial sums of the table above for this rank's rows (to be summed over ranks by the caller) */
+int icrl_ppo_local_advsums(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, double* advsums_out, void* stream);
+/* icrl_ppo_train with the in-kernel gradient all-reduce; per-step stats are this rank's partial sums over the GLOBAL
+ * batch size (sum them over ranks); result[2] != 0 reports a peer time-out. */
+int icrl_ppo_train_dist(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* params, float* adam_m, float* adam_v,
+                        int64_t adam_step_before, float* step_stats, int32_t* result, const icrl_ppo_dist* dist,
+                        void* stream);
+
 /* Policy forward for rollout collection / evaluation (policies.py:716-731 without sampling):
  * head [n, act_out] (action mean or logits), values [n], cost_values [n]; obs is [n, obs_dim] row-major. */
 int icrl_policy_forward(const icrl_ppo_cfg* cfg, const float* params, const float* obs, int64_t n,
