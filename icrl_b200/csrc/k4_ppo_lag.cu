@@ -810,60 +810,85 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
             } else {
                 block_reduce(red);
                 if (working) {
-                    // (1) push this rank's gradient fragments (+ the KL partial) into every rank's receive buffer
-                    const float kl_part = (role == 0 && tid == 0) ? red[3] * invB : 0.f;
-                    const size_t slab = ((size_t)(parity * ICRL_PPO_MAX_RANKS + a.rank) * 3 + role) * DIST_SLOTS * NTT + tid;
-                    for (int p = 0; p < a.world; ++p) {
-                        float* dst = a.recv[p] + slab;
+                    // (1) push this rank's gradient fragments (+ the KL partial) into every rank's receive buffer:
+                    //     128-bit stores, slab layout [float4 slot][thread] so every store instruction is fully coalesced
+                    constexpr int NP = (NTW2 * 4 + NT1 * 4 + 4 + 2 + 3) / 4 * 4;
+                    static_assert(NP <= DIST_SLOTS, "receive-buffer slab too small");
+                    float pay[NP];
+                    {
                         int sl = 0;
 #pragma unroll
                         for (int i = 0; i < NTW2; ++i)
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) dst[(sl++) * NTT] = g_w2[i][c];
+                            for (int c = 0; c < 4; ++c) pay[sl++] = g_w2[i][c];
 #pragma unroll
                         for (int i = 0; i < NT1; ++i)
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) dst[(sl++) * NTT] = g_w1[i][c];
+                            for (int c = 0; c < 4; ++c) pay[sl++] = g_w1[i][c];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) dst[(sl++) * NTT] = g_hw[i];
-                        dst[(sl++) * NTT] = g_s;
-                        dst[(sl++) * NTT] = kl_part;
+                        for (int i = 0; i < 4; ++i) pay[sl++] = g_hw[i];
+                        pay[sl++] = g_s;
+                        pay[sl++] = (role == 0 && tid == 0) ? red[3] * invB : 0.f;     // KL partial of this rank
+#pragma unroll
+                        for (; sl < NP; ++sl) pay[sl] = 0.f;
                     }
-                    __threadfence_system();
-                    __syncthreads();
+                    // "LL" protocol (as NCCL's low-latency path): every 16-byte store carries two values and two copies of
+                    // this step's sequence number, so the data validates itself -- no fence, no separate flag, no barrier:
+                    // the exchange costs one NVLink store latency.  (A torn 16-byte store is still two self-validating
+                    // 8-byte halves.)  Buffers alternate by step parity and the sequence number grows monotonically, so a
+                    // stale slot can never match.
                     const unsigned int want = a.flag_base + (unsigned int)step + 1u;
-                    const int fidx = parity * ICRL_PPO_MAX_RANKS * 4;
-                    if (tid < a.world) st_release_sys(a.flags[tid] + fidx + a.rank * 4 + role, want);
-                    // (2) wait for every rank's flag for this step (spin with a ~2 s budget so a dead peer cannot hang the GPU)
-                    if (tid < a.world) {
-                        const unsigned int* f = a.flags[a.rank] + fidx + tid * 4 + role;
-                        const long long t0 = clock64();
-                        while ((int)(ld_acquire_sys(f) - want) < 0) {
-                            if (clock64() - t0 > 4000000000LL) { XCH[15] = 1.f; break; }
+                    const size_t slab16 = ((size_t)(parity * ICRL_PPO_MAX_RANKS + a.rank) * 3 + role) * (DIST_SLOTS / 2) * NTT;
+                    for (int p = 0; p < a.world; ++p) {
+                        if (p == a.rank) continue;
+                        uint4* dst = reinterpret_cast<uint4*>(a.recv[p]) + slab16 + tid;
+#pragma unroll
+                        for (int k = 0; k < NP / 2; ++k)
+                            dst[k * NTT] = make_uint4(__float_as_uint(pay[2 * k]), want, __float_as_uint(pay[2 * k + 1]), want);
+                    }
+                    // add the partials in rank order (identical on every rank -> bit-identical replicated updates)
+                    float accv[NP];
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) accv[k] = 0.f;
+                    const long long t0 = clock64();
+                    for (int r = 0; r < a.world; ++r) {
+                        if (r == a.rank) {
+#pragma unroll
+                            for (int k = 0; k < NP; ++k) accv[k] += pay[k];
+                            continue;
+                        }
+                        const uint4* src = reinterpret_cast<const uint4*>(a.recv[a.rank]) +
+                                           ((size_t)(parity * ICRL_PPO_MAX_RANKS + r) * 3 + role) * (DIST_SLOTS / 2) * NTT + tid;
+#pragma unroll
+                        for (int k = 0; k < NP / 2; ++k) {
+                            uint4 x;
+                            for (;;) {
+                                asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                             : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "l"(src + k * NTT) : "memory");
+                                if (x.y == want && x.w == want) break;
+                                if (clock64() - t0 > 4000000000LL) { XCH[15] = 1.f; break; }   // ~2 s: a peer is gone
+                            }
+                            accv[2 * k] += __uint_as_float(x.x);
+                            accv[2 * k + 1] += __uint_as_float(x.z);
                         }
                     }
-                    __syncthreads();
-                    // (3) add the partials in rank order (identical on every rank -> bit-identical replicated updates)
-                    const float* src0 = a.recv[a.rank] + ((size_t)(parity * ICRL_PPO_MAX_RANKS) * 3 + role) * DIST_SLOTS * NTT + tid;
-                    const size_t rstride = (size_t)3 * DIST_SLOTS * NTT;
-                    auto gsum = [&](int sl) {
-                        float v = 0.f;
-                        for (int r = 0; r < a.world; ++r) v += __ldcg(src0 + r * rstride + (size_t)sl * NTT);
-                        return v;
-                    };
-                    int sl = 0;
 #pragma unroll
-                    for (int i = 0; i < NTW2; ++i)
+                    for (int k = 0; k < NP; ++k) pay[k] = accv[k];
+                    {
+                        int sl = 0;
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) g_w2[i][c] = gsum(sl++);
+                        for (int i = 0; i < NTW2; ++i)
 #pragma unroll
-                    for (int i = 0; i < NT1; ++i)
+                            for (int c = 0; c < 4; ++c) g_w2[i][c] = pay[sl++];
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) g_w1[i][c] = gsum(sl++);
+                        for (int i = 0; i < NT1; ++i)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) g_hw[i] = gsum(sl++);
-                    g_s = gsum(sl++);
-                    if (role == 0 && tid == 0) scratch[127] = gsum(sl);    // global KL of this step
+                            for (int c = 0; c < 4; ++c) g_w1[i][c] = pay[sl++];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) g_hw[i] = pay[sl++];
+                        g_s = pay[sl++];
+                        if (role == 0 && tid == 0) scratch[127] = pay[sl];    // global KL of this step
+                    }
                 }
                 float r2[6] = {0.f, 0.f, 0.f, 0.f, 0.f, local_sumsq()};
                 block_reduce(r2);

@@ -199,13 +199,13 @@ int icrl_ppo_train(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* pa
  * Data-parallel K4 across the GPUs of one node (one process per GPU).  Every rank owns the rollout
  * of its own environments and runs the same persistent kernel on `batch_size` LOCAL rows per optimiser step; the
  * gradients of the three trunks are summed across ranks INSIDE the kernel: each CTA stores its gradient fragments
- * straight into every peer's receive buffer over NVLink (CUDA IPC mapped memory), raises a per-step flag, waits for the
- * peers' flags and adds the partials in rank order, so all ranks apply bit-identical Adam updates and the replicated
+ * straight into every peer's receive buffer over NVLink (CUDA IPC mapped memory) as self-validating {value, sequence}
+ * words (no fence, no separate flag), polls its own buffer for the peers' words and adds the partials in rank order, so all ranks apply bit-identical Adam updates and the replicated
  * parameters never drift.  The global-minibatch advantage statistics (ppo_lag.py:218-222) are data-only, so the caller
  * all-reduces one small table up front (icrl_ppo_local_advsums -> NCCL all-reduce -> icrl_ppo_dist.advsums).
  */
 #define ICRL_PPO_MAX_RANKS 8
-#define ICRL_PPO_RECV_BYTES (2 * ICRL_PPO_MAX_RANKS * 3 * 72 * 256 * 4) /* [parity][src][trunk][slot][thread] float */
+#define ICRL_PPO_RECV_BYTES (2 * ICRL_PPO_MAX_RANKS * 3 * 72 * 256 * 8) /* [parity][src][trunk][slot pair][thread] {value, seq, value, seq} */
 #define ICRL_PPO_FLAG_BYTES (2 * ICRL_PPO_MAX_RANKS * 4 * 4)             /* [parity][src][trunk] uint32 */
 
 int icrl_comm_alloc(int64_t bytes, void** dev_ptr, unsigned char* handle64);   /* zeroed device buffer + its IPC handle */
