@@ -3,8 +3,8 @@
 // (stable_baselines3/common/buffers.py:493-552), a Python loop over n_steps.
 //
 // A_t = delta_t + c_t * A_{t+1} is an affine recurrence; `done` flags make it segmented (c_t = 0).
-// A CTA owns 32 adjacent env columns (lane = column, so every [T,E] access is a coalesced 128-byte
-// row segment) and NW warps split the time axis into NW chunks:
+// A CTA owns a group of adjacent env columns (32: every [T,E] access is a coalesced 128-byte row segment; 8: four
+// time sub-chunks share a warp) and its threads split the time axis into chunks:
 //   phase 1  each thread folds its chunk into an affine map (M, B):  A_lo = B + M * A_hi      (float64)
 //   phase 2  chunk maps are combined back-to-front through shared memory -> carry-in per chunk
 //   phase 3  the chunk is replayed with the reference's exact operation order and dtypes:
@@ -65,15 +65,21 @@ __device__ __forceinline__ void load_steps(const GaeArgs& a, int t, int col, flo
     sc = gae_step(a.c, a.vc, nvc, alive, last, alive_last, a.g_c, a.gl_c, idx);
 }
 
-template <int NW>
+// CG = env columns per CTA (32: a warp row is one 128-byte segment; 8: four time sub-chunks share a warp, each lane group
+// reading a 32-byte sector -- 4x more chunks and 4x more CTAs for narrow / mid-sized buffers).  NW warps; the time axis is
+// split into NCH = NW * (32 / CG) chunks.
+template <int NW, int CG>
 __global__ void __launch_bounds__(NW * 32) dual_gae_kernel(const GaeArgs a) {
-    __shared__ double sM[2][NW][32], sB[2][NW][32];
+    constexpr int SUB = 32 / CG, NCH = NW * SUB;
+    __shared__ double sM[2][NCH][CG], sB[2][NCH][CG];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int col = blockIdx.x * 32 + lane;
+    const int cl = lane % CG;                       // column within the CTA's group
+    const int ch = w * SUB + lane / CG;             // this thread's time chunk
+    const int col = blockIdx.x * CG + cl;
     const bool active = col < a.E;
     const int T = a.T, E = a.E;
-    const int Lc = (T + NW - 1) / NW;
-    const int lo = w * Lc, hi = min(T, lo + Lc);
+    const int Lc = (T + NCH - 1) / NCH;
+    const int lo = min(T, ch * Lc), hi = min(T, lo + Lc);
 
     double alive_last = 0.0;
     float lvr = 0.f, lvc = 0.f;
@@ -105,15 +111,15 @@ __global__ void __launch_bounds__(NW * 32) dual_gae_kernel(const GaeArgs a) {
             }
         }
     }
-    sM[0][w][lane] = Mr; sB[0][w][lane] = Br;
-    sM[1][w][lane] = Mc; sB[1][w][lane] = Bc;
+    sM[0][ch][cl] = Mr; sB[0][ch][cl] = Br;
+    sM[1][ch][cl] = Mc; sB[1][ch][cl] = Bc;
     __syncthreads();
 
     // ---- phase 2: carry-in of this chunk = composition of all later chunks applied to A_T = 0
     double carry_r = 0.0, carry_c = 0.0;
-    for (int ww = NW - 1; ww > w; --ww) {
-        carry_r = sB[0][ww][lane] + sM[0][ww][lane] * carry_r;
-        carry_c = sB[1][ww][lane] + sM[1][ww][lane] * carry_c;
+    for (int cc = NCH - 1; cc > ch; --cc) {
+        carry_r = sB[0][cc][cl] + sM[0][cc][cl] * carry_r;
+        carry_c = sB[1][cc][cl] + sM[1][cc][cl] * carry_c;
     }
 
     // ---- phase 3: replay with the reference's rounding, store
@@ -149,17 +155,19 @@ __global__ void __launch_bounds__(NW * 32) dual_gae_kernel(const GaeArgs a) {
 
 int dual_gae_device(const GaeArgs& a, cudaStream_t st) {
     if (a.T <= 0 || a.E <= 0) return 0;
-    const int grid = (a.E + 31) / 32;
-    // more warps along time when there are few columns (latency), fewer when the grid already fills the GPU
-    const int64_t work = (int64_t)a.T * a.E;
-    if (a.T >= 1024 && grid < 4 * sm_count()) {
-        dual_gae_kernel<16><<<grid, 16 * 32, 0, st>>>(a);
-    } else if (a.T >= 256 && work < ((int64_t)1 << 26)) {
-        dual_gae_kernel<8><<<grid, 8 * 32, 0, st>>>(a);
-    } else if (a.T >= 64) {
-        dual_gae_kernel<4><<<grid, 4 * 32, 0, st>>>(a);
+    // Few columns: narrow column groups (8 per CTA) and many time chunks, so that short buffers still spread over
+    // many threads / CTAs (the reference's 2048 x 5 buffer is ONE CTA with 64 chunks of 32 steps).  Many columns:
+    // 32-column groups (full 128-byte rows), the grid alone fills the GPU.
+    const int g8 = (a.E + 7) / 8, g32 = (a.E + 31) / 32;
+    if (g32 >= 4 * sm_count()) {
+        if (a.T >= 256) dual_gae_kernel<8, 32><<<g32, 8 * 32, 0, st>>>(a);
+        else dual_gae_kernel<1, 32><<<g32, 32, 0, st>>>(a);
+    } else if (a.T >= 1024) {
+        dual_gae_kernel<16, 8><<<g8, 16 * 32, 0, st>>>(a);
+    } else if (a.T >= 128) {
+        dual_gae_kernel<4, 8><<<g8, 4 * 32, 0, st>>>(a);
     } else {
-        dual_gae_kernel<1><<<grid, 32, 0, st>>>(a);
+        dual_gae_kernel<1, 8><<<g8, 32, 0, st>>>(a);
     }
     ICRL_LAUNCH_CHECK();
     return 0;
