@@ -66,7 +66,7 @@ class PpoDist(C.Structure):
                 ("flag_base", C.c_uint32), ("advsums", c_void)]
 
 
-PPO_RECV_BYTES = 2 * 8 * 3 * 72 * 256 * 8
+PPO_RECV_BYTES = 2 * 8 * 6 * 72 * 256 * 8
 PPO_FLAG_BYTES = 2 * 8 * 4 * 4
 
 # name -> (restype, argtypes); every symbol include/icrl_b200.h declares (checked by tests/test_abi.py)

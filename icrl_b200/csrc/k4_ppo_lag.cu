@@ -99,11 +99,19 @@ __device__ __forceinline__ void warp_gemm_3xtf32(float (&c)[NT][4], const float*
     }
 }
 
+// ---------------------------------------------------------------- geometry of the train kernel
+constexpr int NHALF = 2;       // CTAs per trunk: each takes RBH rows of every 64-row chunk (a CTA pair)
+constexpr int RBH = RB / NHALF;
+constexpr int NCTA = 3 * NHALF; // cluster size
+constexpr int NTT = 256;       // threads of the train kernel: 8 warps (16 warps measured slower: 31.4k vs 27.5k cycles/step on HC)
+constexpr int NWT = NTT / 32;
+constexpr int NTW2 = 4;        // n-tiles of a 64 x 64 output per warp (warp tile 16 x 32)
+
 // ---------------------------------------------------------------- shared memory carve-up (float offsets)
 struct PpoSmem {
-    int w1, w2, b1, b2, hw, hb, logstd, sig, x, h1, h2, dh, rowf, dmean, act, mu, bar, scratch, xch, total_bytes;
+    int w1, w2, b1, b2, hw, hb, logstd, sig, x, h1, h2, dh, rowf, dmean, act, mu, bar, scratch, xch, pay, total_bytes;
 };
-__host__ __device__ inline PpoSmem ppo_smem_layout(int LDX) {
+__host__ __device__ inline PpoSmem ppo_smem_layout(int LDX, int NP) {
     PpoSmem s;
     int o = 0;
     s.w1 = o; o += H * LDX;          // W1[j][k], row stride LDX
@@ -114,17 +122,18 @@ __host__ __device__ inline PpoSmem ppo_smem_layout(int LDX) {
     s.hb = o; o += AMAX;
     s.logstd = o; o += AMAX;
     s.sig = o; o += 2 * AMAX;        // per action dim: 1/sigma^2, log(sigma) -- refreshed by the thread that updates log_std
-    s.x = o; o += 2 * RB * LDX;      // double buffered obs chunks (TMA destinations)
-    s.h1 = o; o += RB * LDH;
-    s.h2 = o; o += RB * LDH;
-    s.dh = o; o += RB * LDH;
-    s.rowf = o; o += 2 * RB * 8;     // per-row scalars of the stream: old_logp, adv_r, adv_c, ret_r, old_vr, ret_c, old_vc, (g)
-    s.dmean = o; o += RB * AMAX;
-    s.act = o; o += 2 * RB * AMAX;
-    s.mu = o; o += RB * AMAX;        // action-head outputs (means / logits)
+    s.x = o; o += 2 * RBH * LDX;      // double buffered obs chunks (TMA destinations)
+    s.h1 = o; o += RBH * LDH;
+    s.h2 = o; o += RBH * LDH;
+    s.dh = o; o += RBH * LDH;
+    s.rowf = o; o += 2 * RBH * 8;    // per-row scalars of the stream: old_logp, adv_r, adv_c, ret_r, old_vr, ret_c, old_vc, (g)
+    s.dmean = o; o += RBH * AMAX;
+    s.act = o; o += 2 * RBH * AMAX;
+    s.mu = o; o += RBH * AMAX;       // action-head outputs (means / logits)
     s.bar = o; o += 4;               // two 8-byte mbarriers (one per chunk buffer)
     s.scratch = o; o += 128;
-    s.xch = o; o += 2 * 4 * 2;       // [parity][rank][{sumsq, stop}]
+    s.xch = o; o += 2 * 8 * 2;       // [parity][cluster rank][{sumsq, stop}]
+    s.pay = o; o += NP * NTT;        // the partner CTA's gradient fragments land here (DSMEM stores)
     s.total_bytes = o * 4;
     return s;
 }
@@ -273,20 +282,20 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
 }
 
 // ---------------------------------------------------------------- the persistent train kernel
-constexpr int NTT = 256;       // threads of the train kernel: 8 warps (16 warps measured slower: 31.4k vs 27.5k cycles/step on HC)
-constexpr int NWT = NTT / 32;
-constexpr int NTW2 = 4;        // n-tiles of a 64 x 64 output per warp (warp tile 16 x 32)
 // NT1 = n-tiles of dW1 (64 x KP) each warp owns (warp w: m-tile w & 3, n-tiles (w >> 2) + 2 i).
-template <int NT1>
+template <int NT1, bool DIST>
 __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant__ PpoArgs a) {
     extern __shared__ __align__(16) float sm[];
     const float nu = a.nu_dev ? *a.nu_dev : a.nu;
     const int LDX = a.DP, KP = a.KP, D = a.D;
-    const PpoSmem L = ppo_smem_layout(LDX);
+    // payload of the pair exchange: gradient fragments + the five loss partial sums (thread 0)
+    constexpr int NP = (NTW2 * 4 + NT1 * 4 + 4 + 1 + 5 + 3) / 4 * 4;
+    const PpoSmem L = ppo_smem_layout(LDX, NP);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int role = (int)cluster_ctarank();        // 0 pi, 1 vf, 2 cvf, >=3 idle (only joins the barriers)
+    const int crank = (int)cluster_ctarank();       // cluster rank: trunk = crank / 2 (0 pi, 1 vf, 2 cvf), half = crank % 2
     const int ncta = (int)cluster_nctarank();
-    const bool working = role < 3;
+    const int role = crank >> 1, half = crank & 1;
+    const bool working = crank < NCTA;
     const int trunk = working ? role : 0;
     const int AOUT = (role == 0) ? a.A : 1;
     const bool has_logstd = (role == 0) && !a.is_discrete;
@@ -299,6 +308,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
     uint64_t* BAR = reinterpret_cast<uint64_t*>(sm + L.bar);
     float* scratch = sm + L.scratch;
     float* XCH = sm + L.xch;
+    float* PAY = sm + L.pay;
 
     // ---- warp tiling of every 64 x 64 (or 64 x KP) GEMM output, and the parameter ownership that follows from it
     const int g = lane >> 2, t = lane & 3;          // mma fragment coordinates
@@ -308,8 +318,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
     const int oj = 16 * mt + g;
     auto w2_k = [&](int nt) { return 32 * ng + 8 * nt + 2 * t; };
     auto w1_k = [&](int i) { return 8 * (ng + 2 * i) + 2 * t; };
-    const bool lowhalf = tid < 256;                 // head / per-row phases use 256 threads (4 per row)
-    const int hd = lowhalf ? (tid >> 4) : AMAX, hk4 = tid & 15;   // head weight: row hd, cols 4*hk4..
+    const int hd = tid >> 4, hk4 = tid & 15;        // head weight: row hd, cols 4*hk4..
     int s_kind = -1, s_idx = 0;                     // scalar slot: b1 | b2 | head bias | log_std
     if (tid < 64) { s_kind = 0; s_idx = tid; }
     else if (tid < 128) { s_kind = 1; s_idx = tid - 64; }
@@ -351,7 +360,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
     }
     if (tid < H) { B1[tid] = 0.f; B2[tid] = 0.f; }
     if (tid < AMAX) { HB[tid] = 0.f; LOGSTD[tid] = 0.f; }
-    if (tid < 16) XCH[tid] = 0.f;
+    if (tid < 32) XCH[tid] = 0.f;
     __syncthreads();
 #pragma unroll
     for (int nt = 0; nt < NTW2; ++nt)
@@ -398,7 +407,10 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
     __syncthreads();
     cluster_sync_all();   // every CTA has zeroed its exchange slots before any peer writes into them
 
-    const int hr = tid >> 2, hq = tid & 3;      // head mapping: row hr, quarter hq
+    const int hr = tid >> 3, hq = tid & 7;      // head mapping: row hr (RBH rows), eighth hq
+    const int mtf = warp & 1, ngf = warp >> 1;  // forward / dH1 tiling of a 32 x 64 output: m-tile, 16-column group
+    const int ojf = 16 * mtf + g;
+    auto fw_k = [&](int nt) { return 16 * ngf + 8 * nt + 2 * t; };
     const int AP = a.AP;
 
     // ---- chunk pipeline: chunk q+1 of the minibatch-ordered streams is fetched by TMA bulk copies (one elected thread,
@@ -412,13 +424,13 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
         return c;
     };
     auto fetch_chunk = [&](const Cursor& c, int buf) {   // called by thread 0 only
-        const size_t p = (size_t)c.epoch * a.N + (size_t)c.mb * a.B + c.c0;   // streams carry RB rows of tail padding
-        const uint32_t xb = RB * LDX * 4, sb = RB * 8 * 4, ab = (role == 0) ? RB * AP * 4 : 0;
+        const size_t p = (size_t)c.epoch * a.N + (size_t)c.mb * a.B + c.c0 + RBH * half;   // streams carry RB rows of tail padding
+        const uint32_t xb = RBH * LDX * 4, sb = RBH * 8 * 4, ab = (role == 0) ? RBH * AP * 4 : 0;
         fence_proxy_async();   // earlier generic-proxy accesses to this buffer are ordered before the async-proxy writes
         mbar_expect_tx(&BAR[buf], xb + sb + ab);
-        bulk_g2s(X + buf * RB * LDX, a.xs + p * LDX, xb, &BAR[buf]);
-        bulk_g2s(ROWF + buf * RB * 8, a.ss + p * 8, sb, &BAR[buf]);
-        if (role == 0) bulk_g2s(ACT + buf * RB * AMAX, a.as + p * AP, ab, &BAR[buf]);
+        bulk_g2s(X + buf * RBH * LDX, a.xs + p * LDX, xb, &BAR[buf]);
+        bulk_g2s(ROWF + buf * RBH * 8, a.ss + p * 8, sb, &BAR[buf]);
+        if (role == 0) bulk_g2s(ACT + buf * RBH * AMAX, a.as + p * AP, ab, &BAR[buf]);
     };
 
     Cursor cur = {0, 0, 0};
@@ -469,11 +481,11 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
 
             if (working) {
                 for (int c0 = 0; c0 < Bn; c0 += RB, ++q) {
-                    const int rows = min(RB, Bn - c0);
+                    const int rows = min(max(min(RB, Bn - c0) - RBH * half, 0), RBH);   // valid rows of THIS CTA's half
                     const int buf = q & 1;
-                    const float* Xc = X + buf * RB * LDX;
-                    float* Rc = ROWF + buf * RB * 8;
-                    const float* Ac = ACT + buf * RB * AMAX;   // rows at stride AP (as the stream stores them)
+                    const float* Xc = X + buf * RBH * LDX;
+                    float* Rc = ROWF + buf * RBH * 8;
+                    const float* Ac = ACT + buf * RBH * AMAX;   // rows at stride AP (as the stream stores them)
                     mbar_wait(&BAR[buf], (uint32_t)((q >> 1) & 1));
                     __syncthreads();          // chunk q landed, and everybody is done with chunk q-1's buffers
                     ICRL_MARK(0)
@@ -486,48 +498,46 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
 
                     // ---- forward layer 1: H1 = tanh(X W1^T + b1)          [warp tile: rows 16mt.., cols 32ng..]
                     {
-                        float acc[NTW2][4];
+                        float acc[2][4];
 #pragma unroll
-                        for (int nt = 0; nt < NTW2; ++nt) {
-                            const float2 b = *reinterpret_cast<const float2*>(B1 + w2_k(nt));
+                        for (int nt = 0; nt < 2; ++nt) {
+                            const float2 b = *reinterpret_cast<const float2*>(B1 + fw_k(nt));
                             acc[nt][0] = b.x; acc[nt][1] = b.y; acc[nt][2] = b.x; acc[nt][3] = b.y;
                         }
-                        warp_gemm_3xtf32<NTW2>(acc, Xc + 16 * mt * LDX, LDX, 1, W1, 1, LDX, KP, 32 * ng, 8, H, g, t);
+                        warp_gemm_3xtf32<2>(acc, Xc + 16 * mtf * LDX, LDX, 1, W1, 1, LDX, KP, 16 * ngf, 8, H, g, t);
 #pragma unroll
-                        for (int nt = 0; nt < NTW2; ++nt) {
-                            *reinterpret_cast<float2*>(H1 + oj * LDH + w2_k(nt)) = make_float2(tanhf(acc[nt][0]), tanhf(acc[nt][1]));
-                            *reinterpret_cast<float2*>(H1 + (oj + 8) * LDH + w2_k(nt)) = make_float2(tanhf(acc[nt][2]), tanhf(acc[nt][3]));
+                        for (int nt = 0; nt < 2; ++nt) {
+                            *reinterpret_cast<float2*>(H1 + ojf * LDH + fw_k(nt)) = make_float2(tanhf(acc[nt][0]), tanhf(acc[nt][1]));
+                            *reinterpret_cast<float2*>(H1 + (ojf + 8) * LDH + fw_k(nt)) = make_float2(tanhf(acc[nt][2]), tanhf(acc[nt][3]));
                         }
                     }
                     __syncthreads();
                     ICRL_MARK(2)
                     // ---- forward layer 2: H2 = tanh(H1 W2^T + b2)
                     {
-                        float acc[NTW2][4];
+                        float acc[2][4];
 #pragma unroll
-                        for (int nt = 0; nt < NTW2; ++nt) {
-                            const float2 b = *reinterpret_cast<const float2*>(B2 + w2_k(nt));
+                        for (int nt = 0; nt < 2; ++nt) {
+                            const float2 b = *reinterpret_cast<const float2*>(B2 + fw_k(nt));
                             acc[nt][0] = b.x; acc[nt][1] = b.y; acc[nt][2] = b.x; acc[nt][3] = b.y;
                         }
-                        warp_gemm_3xtf32<NTW2, H>(acc, H1 + 16 * mt * LDH, LDH, 1, W2, 1, LDH, H, 32 * ng, 8, H, g, t);
+                        warp_gemm_3xtf32<2, H>(acc, H1 + 16 * mtf * LDH, LDH, 1, W2, 1, LDH, H, 16 * ngf, 8, H, g, t);
 #pragma unroll
-                        for (int nt = 0; nt < NTW2; ++nt) {
-                            *reinterpret_cast<float2*>(H2 + oj * LDH + w2_k(nt)) = make_float2(tanhf(acc[nt][0]), tanhf(acc[nt][1]));
-                            *reinterpret_cast<float2*>(H2 + (oj + 8) * LDH + w2_k(nt)) = make_float2(tanhf(acc[nt][2]), tanhf(acc[nt][3]));
+                        for (int nt = 0; nt < 2; ++nt) {
+                            *reinterpret_cast<float2*>(H2 + ojf * LDH + fw_k(nt)) = make_float2(tanhf(acc[nt][0]), tanhf(acc[nt][1]));
+                            *reinterpret_cast<float2*>(H2 + (ojf + 8) * LDH + fw_k(nt)) = make_float2(tanhf(acc[nt][2]), tanhf(acc[nt][3]));
                         }
                     }
                     __syncthreads();
                     ICRL_MARK(3)
 
-                    // ---- heads + losses + d(loss)/d(head output).  4 threads per row (hr, hq).
-                    if (!lowhalf) {
-                        // warps 8-15 have no per-row work in the head phase
-                    } else if (role == 0) {
-                        // action head: outputs d = hq, hq+4, hq+8, hq+12
-                        float out[4];
+                    // ---- heads + losses + d(loss)/d(head output).  8 threads per row (hr < RBH, hq < 8).
+                    if (role == 0) {
+                        // action head: outputs d = hq, hq + 8
+                        float out[2];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int d = hq + 4 * u;
+                        for (int u = 0; u < 2; ++u) {
+                            const int d = hq + 8 * u;
                             float acc = 0.f;
                             if (d < a.A) {
                                 const float4* hrow = reinterpret_cast<const float4*>(H2 + hr * LDH);
@@ -546,13 +556,19 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                         }
                         const bool valid = hr < rows;
                         float logp = 0.f, ent = 0.f;
-                        float dcoef[4] = {0.f, 0.f, 0.f, 0.f};   // d logp / d out[u]
-                        float dent[4] = {0.f, 0.f, 0.f, 0.f};    // d entropy / d out[u] (discrete only)
+                        float dcoef[2] = {0.f, 0.f};   // d logp / d out[u]
+                        float dent[2] = {0.f, 0.f};    // d entropy / d out[u] (discrete only)
+                        auto sum8 = [](float v) {
+                            v += __shfl_xor_sync(0xffffffffu, v, 1);
+                            v += __shfl_xor_sync(0xffffffffu, v, 2);
+                            v += __shfl_xor_sync(0xffffffffu, v, 4);
+                            return v;
+                        };
                         if (!a.is_discrete) {
                             float lp = 0.f, en = 0.f;
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int d = hq + 4 * u;
+                            for (int u = 0; u < 2; ++u) {
+                                const int d = hq + 8 * u;
                                 if (d < a.A) {
                                     const float inv_var = SIG[d], log_scale = SIG[AMAX + d];
                                     const float diff = Ac[hr * AP + d] - out[u];
@@ -561,25 +577,24 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                                     dcoef[u] = diff * inv_var;
                                 }
                             }
-                            lp += __shfl_xor_sync(0xffffffffu, lp, 1); lp += __shfl_xor_sync(0xffffffffu, lp, 2);
-                            en += __shfl_xor_sync(0xffffffffu, en, 1); en += __shfl_xor_sync(0xffffffffu, en, 2);
-                            logp = lp; ent = en;
+                            logp = sum8(lp); ent = sum8(en);
                         } else {
                             float mx = -INFINITY;
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) if (hq + 4 * u < a.A) mx = fmaxf(mx, out[u]);
+                            for (int u = 0; u < 2; ++u) if (hq + 8 * u < a.A) mx = fmaxf(mx, out[u]);
                             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
                             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
                             float se = 0.f;
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) if (hq + 4 * u < a.A) se += expf(out[u] - mx);
-                            se += __shfl_xor_sync(0xffffffffu, se, 1); se += __shfl_xor_sync(0xffffffffu, se, 2);
+                            for (int u = 0; u < 2; ++u) if (hq + 8 * u < a.A) se += expf(out[u] - mx);
+                            se = sum8(se);
                             const float lse = mx + logf(se);
                             const int ai = (int)Ac[hr * AP + 0];
-                            float lp = 0.f, en = 0.f, pr[4], lg[4];
+                            float lp = 0.f, en = 0.f, pr[2], lg[2];
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int d = hq + 4 * u;
+                            for (int u = 0; u < 2; ++u) {
+                                const int d = hq + 8 * u;
                                 pr[u] = 0.f; lg[u] = 0.f;
                                 if (d < a.A) {
                                     lg[u] = out[u] - lse;
@@ -588,12 +603,10 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                                     if (d == ai) lp = lg[u];
                                 }
                             }
-                            lp += __shfl_xor_sync(0xffffffffu, lp, 1); lp += __shfl_xor_sync(0xffffffffu, lp, 2);
-                            en += __shfl_xor_sync(0xffffffffu, en, 1); en += __shfl_xor_sync(0xffffffffu, en, 2);
-                            logp = lp; ent = en;
+                            logp = sum8(lp); ent = sum8(en);
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int d = hq + 4 * u;
+                            for (int u = 0; u < 2; ++u) {
+                                const int d = hq + 8 * u;
                                 if (d < a.A) {
                                     dcoef[u] = (d == ai ? 1.f : 0.f) - pr[u];
                                     dent[u] = -pr[u] * (lg[u] + ent);
@@ -627,24 +640,25 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                         }
                         const float ge = valid ? -a.ent_coef * invB : 0.f;               // d(ent_coef*entropy_loss)/d ent
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int d = hq + 4 * u;
-                            if (d < AMAX) DMEAN[hr * AMAX + d] = (d < a.A) ? (gl * dcoef[u] + ge * dent[u]) : 0.f;
+                        for (int u = 0; u < 2; ++u) {
+                            const int d = hq + 8 * u;
+                            DMEAN[hr * AMAX + d] = (d < a.A) ? (gl * dcoef[u] + ge * dent[u]) : 0.f;
                         }
                         if (hq == 0) Rc[hr * 8 + 7] = gl;
                     } else {
-                        // value head: partial dot over k in [16hq, 16hq+16)
+                        // value head: partial dot over k in [8hq, 8hq+8)
                         float acc = 0.f;
-                        const float4* hrow = reinterpret_cast<const float4*>(H2 + hr * LDH + 16 * hq);
-                        const float4* wrow = reinterpret_cast<const float4*>(HW + 16 * hq);
+                        const float4* hrow = reinterpret_cast<const float4*>(H2 + hr * LDH + 8 * hq);
+                        const float4* wrow = reinterpret_cast<const float4*>(HW + 8 * hq);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
+                        for (int k = 0; k < 2; ++k) {
                             const float4 h = hrow[k], w = wrow[k];
                             acc = fmaf(h.x, w.x, acc); acc = fmaf(h.y, w.y, acc);
                             acc = fmaf(h.z, w.z, acc); acc = fmaf(h.w, w.w, acc);
                         }
                         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
                         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
                         const float V = acc + HB[0];
                         const float target = Rc[hr * 8 + (role == 1 ? 3 : 5)], oldv = Rc[hr * 8 + (role == 1 ? 4 : 6)];
                         const bool clipvf = (role == 1) ? a.has_clip_vf_r : a.has_clip_vf_c;
@@ -671,7 +685,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                     if (hd < AOUT) {
                         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
 #pragma unroll 8
-                        for (int r = 0; r < RB; ++r) {
+                        for (int r = 0; r < RBH; ++r) {
                             const float dm = DMEAN[r * AMAX + hd];
                             const float4 h = *reinterpret_cast<const float4*>(H2 + r * LDH + 4 * hk4);
                             acc0 = fmaf(dm, h.x, acc0); acc1 = fmaf(dm, h.y, acc1);
@@ -682,29 +696,29 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                     if (s_kind == 2) {
                         float acc = 0.f;
 #pragma unroll 8
-                        for (int r = 0; r < RB; ++r) acc += DMEAN[r * AMAX + s_idx];
+                        for (int r = 0; r < RBH; ++r) acc += DMEAN[r * AMAX + s_idx];
                         g_s += acc;
                     } else if (s_kind == 3) {
                         // d logp / d log_std_d = diff^2/var - 1 ; entropy: d(-mean H)/d log_std = -1
                         const float inv_var = SIG[s_idx];
                         float acc = 0.f;
 #pragma unroll 8
-                        for (int r = 0; r < RB; ++r) {
+                        for (int r = 0; r < RBH; ++r) {
                             const float diff = Ac[r * AP + s_idx] - MU[r * AMAX + s_idx];
                             acc = fmaf(Rc[r * 8 + 7], diff * diff * inv_var - 1.f, acc);
                         }
                         g_s += acc - a.ent_coef * (float)rows * invB;
                     }
-                    // ---- dH2pre[r][k] = (sum_d dmean[r][d] * HW[d][k]) * (1 - H2^2)   (thread: row hr, k in [16hq,16hq+16))
-                    if (lowhalf) {
-                        float dloc[16];
+                    // ---- dH2pre[r][k] = (sum_d dmean[r][d] * HW[d][k]) * (1 - H2^2)   (thread: row hr, k in [8hq, 8hq+8))
+                    {
+                        float dloc[8];
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) dloc[k] = 0.f;
+                        for (int k = 0; k < 8; ++k) dloc[k] = 0.f;
                         for (int d = 0; d < AOUT; ++d) {
                             const float dm = DMEAN[hr * AMAX + d];
-                            const float4* wrow = reinterpret_cast<const float4*>(HW + d * WA_LD + 16 * hq);
+                            const float4* wrow = reinterpret_cast<const float4*>(HW + d * WA_LD + 8 * hq);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
+                            for (int k = 0; k < 2; ++k) {
                                 const float4 w = wrow[k];
                                 dloc[4 * k + 0] = fmaf(dm, w.x, dloc[4 * k + 0]);
                                 dloc[4 * k + 1] = fmaf(dm, w.y, dloc[4 * k + 1]);
@@ -712,10 +726,10 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                                 dloc[4 * k + 3] = fmaf(dm, w.w, dloc[4 * k + 3]);
                             }
                         }
-                        const float4* hrow = reinterpret_cast<const float4*>(H2 + hr * LDH + 16 * hq);
-                        float4* drow = reinterpret_cast<float4*>(DH + hr * LDH + 16 * hq);
+                        const float4* hrow = reinterpret_cast<const float4*>(H2 + hr * LDH + 8 * hq);
+                        float4* drow = reinterpret_cast<float4*>(DH + hr * LDH + 8 * hq);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
+                        for (int k = 0; k < 2; ++k) {
                             const float4 h = hrow[k];
                             drow[k] = make_float4(dloc[4 * k + 0] * (1.f - h.x * h.x), dloc[4 * k + 1] * (1.f - h.y * h.y),
                                                   dloc[4 * k + 2] * (1.f - h.z * h.z), dloc[4 * k + 3] * (1.f - h.w * h.w));
@@ -725,48 +739,46 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                     ICRL_MARK(5)
 
                     // ---- dW2[j][k] += sum_r dH2pre[r][j] H1[r][k]   (A = dH2pre^T read in place, B = H1)
-                    warp_gemm_3xtf32<NTW2, RB>(g_w2, DH + 16 * mt, 1, LDH, H1, LDH, 1, RB, 32 * ng, 8, H, g, t);
+                    warp_gemm_3xtf32<NTW2, RBH>(g_w2, DH + 16 * mt, 1, LDH, H1, LDH, 1, RBH, 32 * ng, 8, H, g, t);
                     if (s_kind == 1) {                                   // db2
                         float acc = 0.f;
 #pragma unroll 8
-                        for (int r = 0; r < RB; ++r) acc += DH[r * LDH + s_idx];
+                        for (int r = 0; r < RBH; ++r) acc += DH[r * LDH + s_idx];
                         g_s += acc;
                     }
                     // ---- dH1pre = (dH2pre W2) * (1 - H1^2) -> written over H2      (B[k = j][n = k] = W2[j][k] read in place)
                     {
-                        float acc[NTW2][4];
+                        float acc[2][4];
 #pragma unroll
-                        for (int nt = 0; nt < NTW2; ++nt)
+                        for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
                             for (int c = 0; c < 4; ++c) acc[nt][c] = 0.f;
-                        warp_gemm_3xtf32<NTW2, H>(acc, DH + 16 * mt * LDH, LDH, 1, W2, LDH, 1, H, 32 * ng, 8, H, g, t);
+                        warp_gemm_3xtf32<2, H>(acc, DH + 16 * mtf * LDH, LDH, 1, W2, LDH, 1, H, 16 * ngf, 8, H, g, t);
 #pragma unroll
-                        for (int nt = 0; nt < NTW2; ++nt) {
-                            const float2 ha = *reinterpret_cast<const float2*>(H1 + oj * LDH + w2_k(nt));
-                            const float2 hb = *reinterpret_cast<const float2*>(H1 + (oj + 8) * LDH + w2_k(nt));
-                            *reinterpret_cast<float2*>(H2 + oj * LDH + w2_k(nt)) =
+                        for (int nt = 0; nt < 2; ++nt) {
+                            const float2 ha = *reinterpret_cast<const float2*>(H1 + ojf * LDH + fw_k(nt));
+                            const float2 hb = *reinterpret_cast<const float2*>(H1 + (ojf + 8) * LDH + fw_k(nt));
+                            *reinterpret_cast<float2*>(H2 + ojf * LDH + fw_k(nt)) =
                                 make_float2(acc[nt][0] * (1.f - ha.x * ha.x), acc[nt][1] * (1.f - ha.y * ha.y));
-                            *reinterpret_cast<float2*>(H2 + (oj + 8) * LDH + w2_k(nt)) =
+                            *reinterpret_cast<float2*>(H2 + (ojf + 8) * LDH + fw_k(nt)) =
                                 make_float2(acc[nt][2] * (1.f - hb.x * hb.x), acc[nt][3] * (1.f - hb.y * hb.y));
                         }
                     }
                     __syncthreads();
                     ICRL_MARK(6)
                     // ---- dW1[j][k] += sum_r dH1pre[r][j] X[r][k] ; db1
-                    warp_gemm_3xtf32<NT1, RB>(g_w1, H2 + 16 * mt, 1, LDH, Xc, LDX, 1, RB, 8 * ng, 16, KP, g, t);
+                    warp_gemm_3xtf32<NT1, RBH>(g_w1, H2 + 16 * mt, 1, LDH, Xc, LDX, 1, RBH, 8 * ng, 16, KP, g, t);
                     if (s_kind == 0) {
                         float acc = 0.f;
 #pragma unroll 8
-                        for (int r = 0; r < RB; ++r) acc += H2[r * LDH + s_idx];
+                        for (int r = 0; r < RBH; ++r) acc += H2[r * LDH + s_idx];
                         g_s += acc;
                     }
                     ICRL_MARK(7)
                 }  // chunks
             }      // working
 
-            // ---- block reductions: the five loss partial sums and the sum of squared gradients.  Single GPU: one merged
-            // reduction.  Data parallel: the loss sums first (the pi CTA's KL partial travels with the gradients), then
-            // the in-kernel all-reduce over NVLink peer memory, then the norm of the REDUCED gradient.
+            // ---- (1) block-reduce the five loss partial sums of this CTA's rows
             auto block_reduce = [&](float (&r)[6]) {
 #pragma unroll
                 for (int i = 0; i < 6; ++i) r[i] = warp_sum(r[i]);
@@ -802,137 +814,181 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                 return q2;
             };
             float red[6] = {s_a, s_b, s_c, s_d, s_e, 0.f};
-            float kl_global = 0.f;
-            if (a.world == 1) {
-                red[5] = local_sumsq();
-                block_reduce(red);
-                kl_global = red[3] * invB;
-            } else {
-                block_reduce(red);
-                if (working) {
-                    // (1) push this rank's gradient fragments (+ the KL partial) into every rank's receive buffer:
-                    //     128-bit stores, slab layout [float4 slot][thread] so every store instruction is fully coalesced
-                    constexpr int NP = (NTW2 * 4 + NT1 * 4 + 4 + 2 + 3) / 4 * 4;
-                    static_assert(NP <= DIST_SLOTS, "receive-buffer slab too small");
-                    float pay[NP];
-                    {
-                        int sl = 0;
+            block_reduce(red);
+
+            // ---- (2) CTA-pair exchange through distributed shared memory: every thread stores its gradient fragments (and
+            // thread 0 the loss sums) into the partner's PAY buffer as float4 groups straight from registers, cluster
+            // barrier, add.  a + b == b + a in floating point, so both CTAs of a pair end up with bit-identical sums and
+            // keep their weight copies identical.   Groups: g_w2[0..NTW2), g_w1[0..NT1), g_hw, {g_s, s0, s1, s2}, {s3, s4, -, -}
+            float tot[5] = {red[0], red[1], red[2], red[3], red[4]};      // loss sums: this CTA -> pair -> all ranks
+            if (working) {
+                uint32_t remote;
+                const uint32_t local = smem_u32(PAY + 4 * tid);
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"((uint32_t)(crank ^ 1)));
+                auto st4 = [&](int v4, float x, float y, float z, float w) {
+                    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote + (uint32_t)(v4 * NTT * 16)),
+                                 "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+                };
+                const bool t0 = (tid == 0);
+                int v4 = 0;
 #pragma unroll
-                        for (int i = 0; i < NTW2; ++i)
+                for (int i = 0; i < NTW2; ++i) st4(v4++, g_w2[i][0], g_w2[i][1], g_w2[i][2], g_w2[i][3]);
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) pay[sl++] = g_w2[i][c];
+                for (int i = 0; i < NT1; ++i) st4(v4++, g_w1[i][0], g_w1[i][1], g_w1[i][2], g_w1[i][3]);
+                st4(v4++, g_hw[0], g_hw[1], g_hw[2], g_hw[3]);
+                st4(v4++, g_s, t0 ? tot[0] : 0.f, t0 ? tot[1] : 0.f, t0 ? tot[2] : 0.f);
+                st4(v4++, t0 ? tot[3] : 0.f, t0 ? tot[4] : 0.f, 0.f, 0.f);
+            }
+            cluster_sync_all();
+            if (working) {
+                auto ld4 = [&](int v4) { return *reinterpret_cast<const float4*>(PAY + (v4 * NTT + tid) * 4); };
+                int v4 = 0;
 #pragma unroll
-                        for (int i = 0; i < NT1; ++i)
+                for (int i = 0; i < NTW2; ++i) {
+                    const float4 x = ld4(v4++);
+                    g_w2[i][0] += x.x; g_w2[i][1] += x.y; g_w2[i][2] += x.z; g_w2[i][3] += x.w;
+                }
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) pay[sl++] = g_w1[i][c];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) pay[sl++] = g_hw[i];
-                        pay[sl++] = g_s;
-                        pay[sl++] = (role == 0 && tid == 0) ? red[3] * invB : 0.f;     // KL partial of this rank
-#pragma unroll
-                        for (; sl < NP; ++sl) pay[sl] = 0.f;
-                    }
+                for (int i = 0; i < NT1; ++i) {
+                    const float4 x = ld4(v4++);
+                    g_w1[i][0] += x.x; g_w1[i][1] += x.y; g_w1[i][2] += x.z; g_w1[i][3] += x.w;
+                }
+                {
+                    const float4 x = ld4(v4++);
+                    g_hw[0] += x.x; g_hw[1] += x.y; g_hw[2] += x.z; g_hw[3] += x.w;
+                }
+                {
+                    const float4 x = ld4(v4++), y = ld4(v4++);
+                    g_s += x.x; tot[0] += x.y; tot[1] += x.z; tot[2] += x.w; tot[3] += y.x; tot[4] += y.y;
+                }
+                // ---- (3) data parallel: all-reduce the pair sums across the ranks' matching CTAs over NVLink peer memory
+                if (DIST && a.world > 1) {
                     // "LL" protocol (as NCCL's low-latency path): every 16-byte store carries two values and two copies of
                     // this step's sequence number, so the data validates itself -- no fence, no separate flag, no barrier:
                     // the exchange costs one NVLink store latency.  (A torn 16-byte store is still two self-validating
                     // 8-byte halves.)  Buffers alternate by step parity and the sequence number grows monotonically, so a
-                    // stale slot can never match.
+                    // stale slot can never match.  Every rank also stores into its OWN slab and then sums all slabs in
+                    // rank order from memory: identical order everywhere -> bit-identical replicated updates.
+                    static_assert(NP <= DIST_SLOTS, "receive-buffer slab too small");
                     const unsigned int want = a.flag_base + (unsigned int)step + 1u;
-                    const size_t slab16 = ((size_t)(parity * ICRL_PPO_MAX_RANKS + a.rank) * 3 + role) * (DIST_SLOTS / 2) * NTT;
+                    const size_t slab16 = ((size_t)(parity * ICRL_PPO_MAX_RANKS + a.rank) * NCTA + crank) * (DIST_SLOTS / 2) * NTT;
+                    const bool t0 = (tid == 0);
                     for (int p = 0; p < a.world; ++p) {
-                        if (p == a.rank) continue;
                         uint4* dst = reinterpret_cast<uint4*>(a.recv[p]) + slab16 + tid;
+                        auto put4 = [&](int v4, float x, float y, float z, float w) {
+                            dst[(2 * v4) * NTT] = make_uint4(__float_as_uint(x), want, __float_as_uint(y), want);
+                            dst[(2 * v4 + 1) * NTT] = make_uint4(__float_as_uint(z), want, __float_as_uint(w), want);
+                        };
+                        int v4 = 0;
 #pragma unroll
-                        for (int k = 0; k < NP / 2; ++k)
-                            dst[k * NTT] = make_uint4(__float_as_uint(pay[2 * k]), want, __float_as_uint(pay[2 * k + 1]), want);
+                        for (int i = 0; i < NTW2; ++i) put4(v4++, g_w2[i][0], g_w2[i][1], g_w2[i][2], g_w2[i][3]);
+#pragma unroll
+                        for (int i = 0; i < NT1; ++i) put4(v4++, g_w1[i][0], g_w1[i][1], g_w1[i][2], g_w1[i][3]);
+                        put4(v4++, g_hw[0], g_hw[1], g_hw[2], g_hw[3]);
+                        put4(v4++, g_s, t0 ? tot[0] : 0.f, t0 ? tot[1] : 0.f, t0 ? tot[2] : 0.f);
+                        put4(v4++, t0 ? tot[3] : 0.f, t0 ? tot[4] : 0.f, 0.f, 0.f);
                     }
-                    // add the partials in rank order (identical on every rank -> bit-identical replicated updates)
-                    float accv[NP];
 #pragma unroll
-                    for (int k = 0; k < NP; ++k) accv[k] = 0.f;
-                    const long long t0 = clock64();
+                    for (int i = 0; i < NTW2; ++i)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) g_w2[i][c] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < NT1; ++i)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) g_w1[i][c] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) g_hw[i] = 0.f;
+                    g_s = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) tot[i] = 0.f;
+                    const long long tstart = clock64();
                     for (int r = 0; r < a.world; ++r) {
-                        if (r == a.rank) {
-#pragma unroll
-                            for (int k = 0; k < NP; ++k) accv[k] += pay[k];
-                            continue;
-                        }
                         const uint4* src = reinterpret_cast<const uint4*>(a.recv[a.rank]) +
-                                           ((size_t)(parity * ICRL_PPO_MAX_RANKS + r) * 3 + role) * (DIST_SLOTS / 2) * NTT + tid;
-                        // poll in batches: all loads of a batch are issued before any flag is looked at, so the batch
-                        // costs ONE local-L2 latency instead of one per word (the serial version cost ~16 us at 4 GPUs)
-                        constexpr int PB = 8;
-#pragma unroll
-                        for (int k0 = 0; k0 < NP / 2; k0 += PB) {
-                            uint4 x[PB];
+                                           ((size_t)(parity * ICRL_PPO_MAX_RANKS + r) * NCTA + crank) * (DIST_SLOTS / 2) * NTT + tid;
+                        // poll one float4 group (two 16-byte words) at a time, 4 groups (8 loads) in flight per round trip
+                        auto get4x4 = [&](int v4, float4 (&o)[4], int n) {
+                            uint4 x[8];
                             for (;;) {
                                 bool ok = true;
 #pragma unroll
-                                for (int j = 0; j < PB; ++j)
-                                    if (k0 + j < NP / 2)
+                                for (int j = 0; j < 8; ++j)
+                                    if (j < 2 * n)
                                         asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
                                                      : "=r"(x[j].x), "=r"(x[j].y), "=r"(x[j].z), "=r"(x[j].w)
-                                                     : "l"(src + (k0 + j) * NTT) : "memory");
+                                                     : "l"(src + (2 * v4 + j) * NTT) : "memory");
 #pragma unroll
-                                for (int j = 0; j < PB; ++j)
-                                    if (k0 + j < NP / 2) ok = ok && (x[j].y == want) && (x[j].w == want);
+                                for (int j = 0; j < 8; ++j)
+                                    if (j < 2 * n) ok = ok && (x[j].y == want) && (x[j].w == want);
                                 if (ok) break;
-                                if (clock64() - t0 > 4000000000LL) { XCH[15] = 1.f; break; }   // ~2 s: a peer is gone
+                                if (clock64() - tstart > 4000000000LL) { XCH[31] = 1.f; break; }   // ~2 s: a peer is gone
                             }
 #pragma unroll
-                            for (int j = 0; j < PB; ++j)
-                                if (k0 + j < NP / 2) {
-                                    accv[2 * (k0 + j)] += __uint_as_float(x[j].x);
-                                    accv[2 * (k0 + j) + 1] += __uint_as_float(x[j].z);
+                            for (int j = 0; j < 4; ++j)
+                                if (j < n)
+                                    o[j] = make_float4(__uint_as_float(x[2 * j].x), __uint_as_float(x[2 * j].z),
+                                                       __uint_as_float(x[2 * j + 1].x), __uint_as_float(x[2 * j + 1].z));
+                        };
+                        constexpr int NG = NTW2 + NT1 + 3;       // float4 groups
+                        // walk the groups 4 at a time; the group -> register mapping is resolved at compile time
+#pragma unroll
+                        for (int g0 = 0; g0 < NG; g0 += 4) {
+                            float4 o[4];
+                            get4x4(g0, o, (NG - g0) < 4 ? (NG - g0) : 4);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int gi = g0 + j;
+                                if (gi < NTW2) {
+                                    g_w2[gi][0] += o[j].x; g_w2[gi][1] += o[j].y; g_w2[gi][2] += o[j].z; g_w2[gi][3] += o[j].w;
+                                } else if (gi < NTW2 + NT1) {
+                                    g_w1[gi - NTW2][0] += o[j].x; g_w1[gi - NTW2][1] += o[j].y;
+                                    g_w1[gi - NTW2][2] += o[j].z; g_w1[gi - NTW2][3] += o[j].w;
+                                } else if (gi == NTW2 + NT1) {
+                                    g_hw[0] += o[j].x; g_hw[1] += o[j].y; g_hw[2] += o[j].z; g_hw[3] += o[j].w;
+                                } else if (gi == NTW2 + NT1 + 1) {
+                                    g_s += o[j].x; tot[0] += o[j].y; tot[1] += o[j].z; tot[2] += o[j].w;
+                                } else if (gi == NTW2 + NT1 + 2) {
+                                    tot[3] += o[j].x; tot[4] += o[j].y;
                                 }
+                            }
                         }
                     }
-#pragma unroll
-                    for (int k = 0; k < NP; ++k) pay[k] = accv[k];
-                    {
-                        int sl = 0;
-#pragma unroll
-                        for (int i = 0; i < NTW2; ++i)
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) g_w2[i][c] = pay[sl++];
-#pragma unroll
-                        for (int i = 0; i < NT1; ++i)
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) g_w1[i][c] = pay[sl++];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) g_hw[i] = pay[sl++];
-                        g_s = pay[sl++];
-                        if (role == 0 && tid == 0) scratch[127] = pay[sl];    // global KL of this step
-                    }
                 }
+                if (tid == 0) {
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) scratch[120 + i] = tot[i];   // totals of the pair (and of all ranks in DP mode)
+                }
+            }
+            // ---- (4) norm of the reduced gradient (block reduction; also publishes the loss totals from scratch[120..124])
+            {
                 float r2[6] = {0.f, 0.f, 0.f, 0.f, 0.f, local_sumsq()};
                 block_reduce(r2);
                 red[5] = r2[5];
-                kl_global = scratch[127];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) red[i] = scratch[120 + i];
             }
             const float ss = red[5];
             const size_t so = (size_t)step * ICRL_PPO_STATS_PER_STEP;
             float kl_step = 0.f;
-            if (role == 0) {
+            if (role == 0 && working) {
                 float pl = -(red[0] * invB);
                 pl = pl + nu * (red[1] * invB);
                 pl = pl / (1.f + nu);
-                kl_step = kl_global;
-                if (tid == 0) {
+                kl_step = red[3] * invB;
+                if (tid == 0 && half == 0) {
                     a.stats[so + 0] = pl;
                     a.stats[so + 1] = red[2] * invB;
                     a.stats[so + 4] = -(red[4] * invB);
-                    a.stats[so + 5] = red[3] * invB;
+                    a.stats[so + 5] = kl_step;
                 }
             } else if (working) {
-                if (tid == 0) a.stats[so + (role == 1 ? 2 : 3)] = red[0] * invB;
+                if (tid == 0 && half == 0) a.stats[so + (role == 1 ? 2 : 3)] = red[0] * invB;
             }
             ICRL_MARK(8)
 
-            // ---- global gradient norm: local sum of squares -> DSMEM exchange -> cluster barrier
-            // epoch-level KL early stop is decided by the pi CTA right here (it has this step's KL) and rides along
+            // ---- global gradient norm: every CTA publishes its trunk's sum of squares through DSMEM -> cluster barrier
+            // epoch-level KL early stop is decided by the pi CTAs right here (they have this step's KL) and rides along
             float stop_flag = 0.f;
-            if (role == 0) {
+            if (role == 0 && working) {
                 epoch_kl_sum += (double)kl_step;
                 ++epoch_steps;
                 const bool last_of_epoch = (mb == a.steps_per_epoch - 1);
@@ -940,16 +996,16 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                 if (a.max_steps > 0 && step + 1 >= a.max_steps) stop_flag = 2.f;
             }
             if (tid < ncta && working) {
-                st_remote_f32(XCH + (parity * 4 + role) * 2 + 0, (uint32_t)tid, ss);
-                st_remote_f32(XCH + (parity * 4 + role) * 2 + 1, (uint32_t)tid, stop_flag);
+                st_remote_f32(XCH + (parity * 8 + crank) * 2 + 0, (uint32_t)tid, ss);
+                st_remote_f32(XCH + (parity * 8 + crank) * 2 + 1, (uint32_t)tid, stop_flag);
             }
             cluster_sync_all();
             ICRL_MARK(9)
-            const float total_ss = XCH[(parity * 4 + 0) * 2] + XCH[(parity * 4 + 1) * 2] + XCH[(parity * 4 + 2) * 2];
-            const float stop_rx = XCH[(parity * 4 + 0) * 2 + 1];
+            const float total_ss = XCH[(parity * 8 + 0) * 2] + XCH[(parity * 8 + 2) * 2] + XCH[(parity * 8 + 4) * 2];
+            const float stop_rx = XCH[(parity * 8 + 0) * 2 + 1];
             const float total_norm = sqrtf(total_ss);
             const float clip_coef = fminf(a.max_grad_norm / (total_norm + 1e-6f), 1.0f);
-            if (role == 0 && tid == 0) {
+            if (crank == 0 && tid == 0) {
                 a.stats[so + 7] = total_norm;
                 a.stats[so + 6] = 0.f;   // total loss is assembled on the host from the parts (needs all three CTAs)
             }
@@ -1014,12 +1070,12 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
     if (working && cur_valid(cur)) mbar_wait(&BAR[q & 1], (uint32_t)((q >> 1) & 1));   // drain the in-flight prefetch
     __syncthreads();
     if (timed) {
-        for (int i = 0; i < 16; ++i) a.timing[role * 16 + i] = tacc[i];
+        for (int i = 0; i < 16; ++i) a.timing[crank * 16 + i] = tacc[i];
     }
 #undef ICRL_MARK
 
-    // ---- write back parameters and moments (owner threads)
-    if (working) {
+    // ---- write back parameters and moments (owner threads of the first CTA of each pair; the second holds identical copies)
+    if (working && half == 0) {
 #pragma unroll
         for (int nt = 0; nt < NTW2; ++nt)
 #pragma unroll
@@ -1045,10 +1101,10 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
             a.params[f] = *slot; a.adam_m[f] = m_s; a.adam_v[f] = v_s;
         }
     }
-    if (role == 0 && tid == 0) {
+    if (crank == 0 && tid == 0) {
         a.result[0] = early_stop_epoch;
         a.result[1] = step;
-        a.result[2] = (XCH[15] != 0.f) ? 1 : 0;   // a peer timed out in data-parallel mode
+        a.result[2] = (XCH[31] != 0.f) ? 1 : 0;   // a peer timed out in data-parallel mode
         a.result[3] = 0;
     }
     cluster_sync_all();   // nobody exits while a peer may still address its shared memory
@@ -1057,32 +1113,28 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
 // ---------------------------------------------------------------- host side
 template <int NT1>
 static int launch_ppo(const PpoArgs& a, cudaStream_t st) {
-    auto kern = ppo_train_kernel<NT1>;
-    const PpoSmem L = ppo_smem_layout(a.DP);
+    auto kern = a.world > 1 ? ppo_train_kernel<NT1, true> : ppo_train_kernel<NT1, false>;
+    constexpr int NP = (NTW2 * 4 + NT1 * 4 + 4 + 1 + 5 + 3) / 4 * 4;
+    const PpoSmem L = ppo_smem_layout(a.DP, NP);
     if (L.total_bytes > 227 * 1024) {
         set_error("obs_dim %d needs %d bytes of shared memory (> 227 KB)", a.D, L.total_bytes);
         return ICRL_EUNSUPPORTED;
     }
     ICRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes));
-    cudaError_t err = cudaErrorUnknown;
-    // one CTA per trunk; clusters of 3 are legal, but fall back to 4 (one idle CTA) should a driver refuse
-    for (int cluster = 3; cluster <= 4; ++cluster) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(cluster);
-        cfg.blockDim = dim3(NTT);
-        cfg.dynamicSmemBytes = L.total_bytes;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = cluster;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        err = cudaLaunchKernelEx(&cfg, kern, a);
-        if (err == cudaSuccess) break;
-        (void)cudaGetLastError();
-    }
+    // one cluster of 6 CTAs: a CTA pair per trunk (pi, vf, cvf)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(NCTA);
+    cfg.blockDim = dim3(NTT);
+    cfg.dynamicSmemBytes = L.total_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NCTA;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t err = cudaLaunchKernelEx(&cfg, kern, a);
     if (err != cudaSuccess) {
         set_error("ppo_train_kernel launch failed: %s", cudaGetErrorString(err));
         return (int)err;
@@ -1157,7 +1209,7 @@ static int ppo_train_impl(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, fl
     }
     static unsigned long long* timing_dev = nullptr;
     const bool want_timing = getenv("ICRL_PPO_TIMING") != nullptr;
-    if (want_timing && !timing_dev) cudaMalloc(&timing_dev, 48 * sizeof(unsigned long long));
+    if (want_timing && !timing_dev) cudaMalloc(&timing_dev, 128 * sizeof(unsigned long long));
     a.timing = want_timing ? timing_dev : nullptr;
     const int n_tiles = a.KP / 8;                 // n-tiles of dW1; each warp owns every second one
     const int nt1 = (n_tiles + 1) / 2;
@@ -1165,20 +1217,19 @@ static int ppo_train_impl(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, fl
     else if (nt1 <= 2) rc = icrl::launch_ppo<2>(a, st);
     else if (nt1 <= 4) rc = icrl::launch_ppo<4>(a, st);
     else if (nt1 <= 8) rc = icrl::launch_ppo<8>(a, st);
-    else if (nt1 <= 12) rc = icrl::launch_ppo<12>(a, st);
     else {
-        icrl::set_error("obs_dim %d too large for the PPO kernel (max 192)", a.D);
+        icrl::set_error("obs_dim %d too large for the PPO kernel (max 128)", a.D);
         return ICRL_EUNSUPPORTED;
     }
     if (rc == 0 && want_timing) {   // profiling aid: per-phase cycles of thread 0 of each trunk CTA (synchronises!)
-        unsigned long long h[48];
+        unsigned long long h[128];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, timing_dev, sizeof(h), cudaMemcpyDeviceToHost);
         const char* names[11] = {"wait+sync", "prefetch", "L1", "L2", "head", "headgrad+dH2", "dW2+dH1", "dW1", "reduce+stats",
                                  "xchg+cluster", "adam"};
         const double steps = (double)(a.max_steps > 0 ? a.max_steps : a.n_epochs * a.steps_per_epoch);
-        for (int r = 0; r < 3; ++r) {
-            fprintf(stderr, "[ppo timing] role %d cycles/step:", r);
+        for (int r = 0; r < icrl::NCTA; r += (r == 0 ? 1 : 2)) {
+            fprintf(stderr, "[ppo timing] cta %d cycles/step:", r);
             double tot = 0;
             for (int i = 0; i < 11; ++i) { fprintf(stderr, " %s=%.0f", names[i], h[r * 16 + i] / steps); tot += h[r * 16 + i] / steps; }
             fprintf(stderr, " total=%.0f\n", tot);

@@ -205,7 +205,7 @@ int icrl_ppo_train(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* pa
  * all-reduces one small table up front (icrl_ppo_local_advsums -> NCCL all-reduce -> icrl_ppo_dist.advsums).
  */
 #define ICRL_PPO_MAX_RANKS 8
-#define ICRL_PPO_RECV_BYTES (2 * ICRL_PPO_MAX_RANKS * 3 * 72 * 256 * 8) /* [parity][src][trunk][slot pair][thread] {value, seq, value, seq} */
+#define ICRL_PPO_RECV_BYTES (2 * ICRL_PPO_MAX_RANKS * 6 * 72 * 256 * 8) /* [parity][src][cta of the 6-CTA cluster][slot pair][thread] {value, seq, value, seq} */
 #define ICRL_PPO_FLAG_BYTES (2 * ICRL_PPO_MAX_RANKS * 4 * 4)             /* [parity][src][trunk] uint32 */
 
 int icrl_comm_alloc(int64_t bytes, void** dev_ptr, unsigned char* handle64);   /* zeroed device buffer + its IPC handle */

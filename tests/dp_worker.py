@@ -74,8 +74,7 @@ def main():
     dist.all_gather(allp, mine)
     for r in range(world):
         assert th.equal(allp[r], allp[0]), f"rank {r} parameters drifted"
-    # global per-step stats = sum of the ranks' partials
-    dist.all_reduce(stats)
+    # per-step stats are global already (the loss sums ride along with the gradient all-reduce)
     if rank == 0:
         th.set_num_threads(1)
         flat = {k: ogae.env_major(v) for k, v in g.items()}
