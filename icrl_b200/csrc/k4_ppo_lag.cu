@@ -146,8 +146,11 @@ __device__ __forceinline__ float adam_update(float p, float g, float& m, float& 
     m = fmaf(c.one_minus_b1, g - m, m);                        // exp_avg.lerp_(grad, 1 - beta1)
     v = fmaf(c.one_minus_b2 * g, g, v * c.b2);                 // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
     // (sqrt(v) / sqrt(bc2)).add_(eps); param.addcdiv_(m, denom, value=-step_size).  The two divisions are done as a
-    // multiply by the precomputed reciprocal and a 2-ulp fast division: <= 3e-7 relative on an lr-sized update.
-    const float denom = fmaf(sqrtf(v), c.inv_bc2_sqrt, c.eps);
+    // multiply by the precomputed reciprocal, an approximate square root and a 2-ulp fast division: <= 5e-7 relative on
+    // an lr-sized update.
+    float sq;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(v));       // one MUFU op, <= 2 ulp (sqrtf's IEEE path costs ~8 instructions)
+    const float denom = fmaf(sq, c.inv_bc2_sqrt, c.eps);
     return fmaf(c.neg_step_size, __fdividef(m, denom), p);
 }
 
@@ -479,8 +482,20 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                         adv_mean_c = a.advstats[step * 8 + 2];
             const float adam_inv_bc2_sqrt = a.advstats[step * 8 + 3], adam_neg_step = a.advstats[step * 8 + 4];
 
+            // DSMEM address of this thread's slot in the PARTNER CTA's PAY buffer; gradient groups are pushed as soon as
+            // they are final (asynchronous stores that overlap the rest of the backward pass)
+            uint32_t pay_remote = 0;
+            if (working) {
+                const uint32_t local = smem_u32(PAY + 4 * tid);
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(pay_remote) : "r"(local), "r"((uint32_t)(crank ^ 1)));
+            }
+            auto st4 = [&](int v4, float x, float y, float z, float w) {
+                asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(pay_remote + (uint32_t)(v4 * NTT * 16)),
+                             "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+            };
             if (working) {
                 for (int c0 = 0; c0 < Bn; c0 += RB, ++q) {
+                    const bool last_chunk = (c0 + RB >= Bn);
                     const int rows = min(max(min(RB, Bn - c0) - RBH * half, 0), RBH);   // valid rows of THIS CTA's half
                     const int buf = q & 1;
                     const float* Xc = X + buf * RBH * LDX;
@@ -740,6 +755,11 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
 
                     // ---- dW2[j][k] += sum_r dH2pre[r][j] H1[r][k]   (A = dH2pre^T read in place, B = H1)
                     warp_gemm_3xtf32<NTW2, RBH>(g_w2, DH + 16 * mt, 1, LDH, H1, LDH, 1, RBH, 32 * ng, 8, H, g, t);
+                    if (last_chunk) {
+#pragma unroll
+                        for (int i = 0; i < NTW2; ++i) st4(i, g_w2[i][0], g_w2[i][1], g_w2[i][2], g_w2[i][3]);
+                        st4(NTW2 + NT1, g_hw[0], g_hw[1], g_hw[2], g_hw[3]);
+                    }
                     if (s_kind == 1) {                                   // db2
                         float acc = 0.f;
 #pragma unroll 8
@@ -813,31 +833,23 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                 }
                 return q2;
             };
-            float red[6] = {s_a, s_b, s_c, s_d, s_e, 0.f};
-            block_reduce(red);
+            // loss partial sums: warp-reduce only; lane 0 of every warp carries its warp's partial through the exchanges
+            // (slot-wise sums), the single block reduction after the exchanges totals them together with the gradient norm
+            float red[6] = {warp_sum(s_a), warp_sum(s_b), warp_sum(s_c), warp_sum(s_d), warp_sum(s_e), 0.f};
 
             // ---- (2) CTA-pair exchange through distributed shared memory: every thread stores its gradient fragments (and
             // thread 0 the loss sums) into the partner's PAY buffer as float4 groups straight from registers, cluster
             // barrier, add.  a + b == b + a in floating point, so both CTAs of a pair end up with bit-identical sums and
             // keep their weight copies identical.   Groups: g_w2[0..NTW2), g_w1[0..NT1), g_hw, {g_s, s0, s1, s2}, {s3, s4, -, -}
-            float tot[5] = {red[0], red[1], red[2], red[3], red[4]};      // loss sums: this CTA -> pair -> all ranks
+            float tot[5];                                                 // loss sums: this warp -> pair -> all ranks
+#pragma unroll
+            for (int i = 0; i < 5; ++i) tot[i] = (lane == 0) ? red[i] : 0.f;
             if (working) {
-                uint32_t remote;
-                const uint32_t local = smem_u32(PAY + 4 * tid);
-                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"((uint32_t)(crank ^ 1)));
-                auto st4 = [&](int v4, float x, float y, float z, float w) {
-                    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote + (uint32_t)(v4 * NTT * 16)),
-                                 "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
-                };
-                const bool t0 = (tid == 0);
-                int v4 = 0;
+                const bool t0 = true;   // every thread sends its slot (non-zero for lane 0 of each warp)
 #pragma unroll
-                for (int i = 0; i < NTW2; ++i) st4(v4++, g_w2[i][0], g_w2[i][1], g_w2[i][2], g_w2[i][3]);
-#pragma unroll
-                for (int i = 0; i < NT1; ++i) st4(v4++, g_w1[i][0], g_w1[i][1], g_w1[i][2], g_w1[i][3]);
-                st4(v4++, g_hw[0], g_hw[1], g_hw[2], g_hw[3]);
-                st4(v4++, g_s, t0 ? tot[0] : 0.f, t0 ? tot[1] : 0.f, t0 ? tot[2] : 0.f);
-                st4(v4++, t0 ? tot[3] : 0.f, t0 ? tot[4] : 0.f, 0.f, 0.f);
+                for (int i = 0; i < NT1; ++i) st4(NTW2 + i, g_w1[i][0], g_w1[i][1], g_w1[i][2], g_w1[i][3]);
+                st4(NTW2 + NT1 + 1, g_s, t0 ? tot[0] : 0.f, t0 ? tot[1] : 0.f, t0 ? tot[2] : 0.f);
+                st4(NTW2 + NT1 + 2, t0 ? tot[3] : 0.f, t0 ? tot[4] : 0.f, 0.f, 0.f);
             }
             cluster_sync_all();
             if (working) {
@@ -872,7 +884,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                     static_assert(NP <= DIST_SLOTS, "receive-buffer slab too small");
                     const unsigned int want = a.flag_base + (unsigned int)step + 1u;
                     const size_t slab16 = ((size_t)(parity * ICRL_PPO_MAX_RANKS + a.rank) * NCTA + crank) * (DIST_SLOTS / 2) * NTT;
-                    const bool t0 = (tid == 0);
+                    const bool t0 = true;
                     for (int p = 0; p < a.world; ++p) {
                         uint4* dst = reinterpret_cast<uint4*>(a.recv[p]) + slab16 + tid;
                         auto put4 = [&](int v4, float x, float y, float z, float w) {
@@ -953,18 +965,13 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                         }
                     }
                 }
-                if (tid == 0) {
-#pragma unroll
-                    for (int i = 0; i < 5; ++i) scratch[120 + i] = tot[i];   // totals of the pair (and of all ranks in DP mode)
-                }
             }
             // ---- (4) norm of the reduced gradient (block reduction; also publishes the loss totals from scratch[120..124])
             {
-                float r2[6] = {0.f, 0.f, 0.f, 0.f, 0.f, local_sumsq()};
+                float r2[6] = {tot[0], tot[1], tot[2], tot[3], tot[4], local_sumsq()};
                 block_reduce(r2);
-                red[5] = r2[5];
 #pragma unroll
-                for (int i = 0; i < 5; ++i) red[i] = scratch[120 + i];
+                for (int i = 0; i < 6; ++i) red[i] = r2[i];
             }
             const float ss = red[5];
             const size_t so = (size_t)step * ICRL_PPO_STATS_PER_STEP;
