@@ -917,25 +917,25 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                     for (int r = 0; r < a.world; ++r) {
                         const uint4* src = reinterpret_cast<const uint4*>(a.recv[a.rank]) +
                                            ((size_t)(parity * ICRL_PPO_MAX_RANKS + r) * NCTA + crank) * (DIST_SLOTS / 2) * NTT + tid;
-                        // poll one float4 group (two 16-byte words) at a time, 4 groups (8 loads) in flight per round trip
-                        auto get4x4 = [&](int v4, float4 (&o)[4], int n) {
-                            uint4 x[8];
+                        // 8 float4 groups (16 sixteen-byte words) in flight per polling round trip
+                        auto get4x4 = [&](int v4, float4 (&o)[8], int n) {
+                            uint4 x[16];
                             for (;;) {
                                 bool ok = true;
 #pragma unroll
-                                for (int j = 0; j < 8; ++j)
+                                for (int j = 0; j < 16; ++j)
                                     if (j < 2 * n)
                                         asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
                                                      : "=r"(x[j].x), "=r"(x[j].y), "=r"(x[j].z), "=r"(x[j].w)
                                                      : "l"(src + (2 * v4 + j) * NTT) : "memory");
 #pragma unroll
-                                for (int j = 0; j < 8; ++j)
+                                for (int j = 0; j < 16; ++j)
                                     if (j < 2 * n) ok = ok && (x[j].y == want) && (x[j].w == want);
                                 if (ok) break;
                                 if (clock64() - tstart > 4000000000LL) { XCH[31] = 1.f; break; }   // ~2 s: a peer is gone
                             }
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
+                            for (int j = 0; j < 8; ++j)
                                 if (j < n)
                                     o[j] = make_float4(__uint_as_float(x[2 * j].x), __uint_as_float(x[2 * j].z),
                                                        __uint_as_float(x[2 * j + 1].x), __uint_as_float(x[2 * j + 1].z));
@@ -943,11 +943,11 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                         constexpr int NG = NTW2 + NT1 + 3;       // float4 groups
                         // walk the groups 4 at a time; the group -> register mapping is resolved at compile time
 #pragma unroll
-                        for (int g0 = 0; g0 < NG; g0 += 4) {
-                            float4 o[4];
-                            get4x4(g0, o, (NG - g0) < 4 ? (NG - g0) : 4);
+                        for (int g0 = 0; g0 < NG; g0 += 8) {
+                            float4 o[8];
+                            get4x4(g0, o, (NG - g0) < 8 ? (NG - g0) : 8);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
+                            for (int j = 0; j < 8; ++j) {
                                 const int gi = g0 + j;
                                 if (gi < NTW2) {
                                     g_w2[gi][0] += o[j].x; g_w2[gi][1] += o[j].y; g_w2[gi][2] += o[j].z; g_w2[gi][3] += o[j].w;
