@@ -55,7 +55,9 @@ class _FlatAdam:
         for k in ("lr", "eps", "betas"):
             if k in g:
                 self.param_groups[0][k] = tuple(g[k]) if k == "betas" else g[k]
-        keys = sorted(sd["state"].keys())
+        # torch >= 1.? numbers the state 0..n-1; older checkpoints (the reference's expert zips) key it by id(param)
+        # and give the parameter order in param_groups[0]['params']
+        keys = [k for k in g.get("params", []) if k in sd["state"]] or sorted(sd["state"].keys())
         for i, ((off, shape), k) in enumerate(zip(self._owner._param_slices(), keys)):
             n = int(np.prod(shape))
             st = sd["state"][k]

@@ -40,3 +40,25 @@ def dump(step=0):
 
 def get_log_dict():
     return Logger.CURRENT.name_to_value
+
+
+class HumanOutputFormat:
+    """Plain key/value table on a text stream (logger.py HumanOutputFormat: write(key_values, key_excluded, step))."""
+
+    def __init__(self, stream):
+        self.stream = stream
+
+    def write(self, key_values, key_excluded=None, step=0):
+        rows = []
+        for k, v in sorted(key_values.items()):
+            if key_excluded and key_excluded.get(k) and "stdout" in str(key_excluded[k]):
+                continue
+            if hasattr(v, "item") and getattr(v, "ndim", 0) == 0:
+                v = v.item()
+            rows.append((str(k), "%-8.3g" % v if isinstance(v, float) else str(v)))
+        if not rows:
+            return
+        kw, vw = max(len(k) for k, _ in rows), max(len(v) for _, v in rows)
+        bar = "-" * (kw + vw + 7)
+        self.stream.write("\n".join([bar] + ["| %-*s | %-*s |" % (kw, k, vw, v) for k, v in rows] + [bar]) + "\n")
+        self.stream.flush()

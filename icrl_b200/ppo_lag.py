@@ -8,6 +8,7 @@ stop.  The dual step (dual_variable.py:47-57) follows as a second tiny launch.  
 keep the reference's control flow; env stepping stays on the host (north_star (c)).
 """
 import ctypes as C
+import os
 import time
 from typing import Any, Callable, Dict, Optional, Union
 
@@ -376,7 +377,118 @@ class PPOLagrangian:
     def predict(self, observation, state=None, mask=None, deterministic: bool = False):
         return self.policy.predict(observation, state, mask, deterministic)
 
-    # ---------------------------------------------------------------- checkpoints (tensors only)
+    # ---------------------------------------------------------------- checkpoints (base_class.py:564-700, save_util.py)
+    _SAVED_SCALARS = ("algo_type", "learning_rate", "n_steps", "batch_size", "n_epochs", "reward_gamma",
+                      "reward_gae_lambda", "cost_gamma", "cost_gae_lambda", "ent_coef", "reward_vf_coef", "cost_vf_coef",
+                      "max_grad_norm", "target_kl", "penalty_initial_value", "penalty_learning_rate",
+                      "penalty_min_value", "update_penalty_after", "budget", "seed", "n_envs", "num_timesteps",
+                      "_total_timesteps", "_n_updates", "_current_progress_remaining", "use_sde", "policy_kwargs",
+                      "pid_kwargs")
+
+    def save(self, path: str) -> None:
+        """Write the reference's zip layout: `data` (JSON), `policy.pth`, `policy.optimizer.pth`,
+        `pytorch_variables.pth`, `_stable_baselines3_version`.  `data` holds plain JSON values only (the reference
+        cloudpickles spaces / schedules into it; here the spaces are stored as shape/bounds and the schedules as their
+        value at progress 1)."""
+        import io, json, zipfile
+        path = str(path)
+        if not path.endswith(".zip"):
+            path += ".zip"
+        data = {}
+        for k in self._SAVED_SCALARS:
+            v = getattr(self, k, None)
+            data[k] = v if not callable(v) else float(v(1))
+        for k in ("clip_range", "clip_range_reward_vf", "clip_range_cost_vf"):
+            v = getattr(self, k)
+            data[k] = None if v is None else float(v(1)) if callable(v) else v
+        osp, asp = self.observation_space, self.action_space
+        data["observation_space"] = dict(shape=list(osp.shape))
+        data["action_space"] = (dict(n=int(asp.n)) if _is_discrete(asp) else
+                                dict(shape=list(asp.shape), low=np.asarray(asp.low).tolist(),
+                                     high=np.asarray(asp.high).tolist()))
+        data["policy_class"] = next((k for k, v in POLICIES.items() if v is self.policy_class), "TwoCriticsMlpPolicy")
+
+        def blob(obj):
+            buf = io.BytesIO()
+            th.save(obj, buf)
+            return buf.getvalue()
+        variables = {}
+        if isinstance(self.dual, DualVariable):
+            variables = dict(dual_state=self.dual.nu.state.detach().cpu(), dual_steps=self.dual.steps)
+        os_dir = os.path.dirname(path)
+        if os_dir:
+            os.makedirs(os_dir, exist_ok=True)
+        with zipfile.ZipFile(path, "w") as zf:
+            zf.writestr("data", json.dumps(data, indent=4, default=str))
+            zf.writestr("policy.pth", blob(self.policy.state_dict()))
+            zf.writestr("policy.optimizer.pth", blob(self.policy.optimizer.state_dict()))
+            zf.writestr("pytorch_variables.pth", blob(variables))
+            zf.writestr("_stable_baselines3_version", "0.9.0a2+icrl_b200")
+
+    @classmethod
+    def load(cls, path: str, env=None, device="auto", **kwargs) -> "PPOLagrangian":
+        """Load a zip written by `save` OR by the reference (its expert `best_model.zip` files): the tensors come
+        from `policy.pth` / `policy.optimizer.pth`; hyper-parameters from the plain-JSON entries of `data`; the
+        observation / action spaces from `env`, from `data`, or -- for reference zips, whose spaces are cloudpickled
+        gym objects -- from the parameter shapes."""
+        import io, json, zipfile
+        from .spaces import Box, Discrete
+        path = str(path)
+        if not os.path.exists(path) and os.path.exists(path + ".zip"):
+            path += ".zip"
+        with zipfile.ZipFile(path) as zf:
+            data = json.loads(zf.read("data"))
+            sd = th.load(io.BytesIO(zf.read("policy.pth")), map_location="cpu", weights_only=False)
+            names = zf.namelist()
+            osd = (th.load(io.BytesIO(zf.read("policy.optimizer.pth")), map_location="cpu", weights_only=False)
+                   if "policy.optimizer.pth" in names else None)
+            variables = (th.load(io.BytesIO(zf.read("pytorch_variables.pth")), map_location="cpu", weights_only=False)
+                         if "pytorch_variables.pth" in names else {})
+
+        def plain(k, default=None):
+            v = data.get(k, default)
+            return default if isinstance(v, dict) and ":serialized:" in v else v
+        obs_dim = sd["mlp_extractor.policy_net.0.weight"].shape[1]
+        act_out = sd["action_net.weight"].shape[0]
+        if env is not None:
+            osp, asp = env.observation_space, env.action_space
+        else:
+            o, a = plain("observation_space"), plain("action_space")
+            osp = Box(-np.inf, np.inf, shape=tuple(o["shape"]) if o else (obs_dim,))
+            if a is not None:
+                asp = Discrete(a["n"]) if "n" in a else Box(np.asarray(a["low"], np.float32),
+                                                            np.asarray(a["high"], np.float32))
+            else:   # reference zip: continuous heads carry log_std; bounds unknown -> unbounded box
+                asp = Box(-np.inf, np.inf, shape=(act_out,)) if "log_std" in sd else Discrete(act_out)
+
+        class _Spaces:
+            observation_space, action_space, num_envs = osp, asp, int(plain("n_envs", 1) or 1)
+        ctor = {k: plain(k) for k in ("algo_type", "learning_rate", "n_steps", "batch_size", "n_epochs", "reward_gamma",
+                                      "reward_gae_lambda", "cost_gamma", "cost_gae_lambda", "clip_range",
+                                      "clip_range_reward_vf", "clip_range_cost_vf", "ent_coef", "reward_vf_coef",
+                                      "cost_vf_coef", "max_grad_norm", "target_kl", "penalty_initial_value",
+                                      "penalty_learning_rate", "penalty_min_value", "update_penalty_after", "budget",
+                                      "seed", "policy_kwargs", "pid_kwargs") if plain(k) is not None}
+        ctor.update(kwargs)
+        if ctor.get("algo_type") == "pidlagrangian" and not ctor.get("pid_kwargs"):
+            ctor["algo_type"] = "lagrangian"                        # PID state of a reference zip is not recoverable
+        seed = ctor.pop("seed", None)
+        model = cls(policy=POLICIES.get(plain("policy_class"), ActorTwoCriticsPolicy), env=env or _Spaces(),
+                    device=device, seed=None, **ctor)
+        model.seed = seed
+        if env is None:
+            model.env = None
+        model.policy.load_state_dict(sd)
+        if osd is not None and osd.get("state"):
+            model.policy.optimizer.load_state_dict(osd)
+        if "dual_state" in variables and isinstance(model.dual, DualVariable):
+            model.dual.nu.state.copy_(variables["dual_state"])
+            model.dual.steps = int(variables["dual_steps"])
+        for k in ("num_timesteps", "_total_timesteps", "_n_updates", "_current_progress_remaining"):
+            if plain(k) is not None:
+                setattr(model, k, plain(k))
+        return model
+
     def get_parameters(self):
         return {"policy": self.policy.state_dict(), "policy.optimizer": self.policy.optimizer.state_dict()}
 

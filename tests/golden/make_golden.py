@@ -297,6 +297,97 @@ def golden_k4():
         save(f"k4_{name}", **arrays)
 
 
+# ------------------------------------------------------------------------------------------- VecEnv wrappers
+def golden_venv():
+    """Reference VecCostWrapper + VecNormalizeWithCost driven by the scripted env (tests/golden/scripted_env.py)."""
+    sys.path.insert(0, OUT)
+    from scripted_env import ScriptedEnv, scripted_actions, scripted_cost
+    from stable_baselines3.common.vec_env import VecCostWrapper, VecNormalizeWithCost, sync_envs_normalization
+    n_envs, steps = 3, 120
+    for name, kw in {"all": dict(norm_obs=True, norm_reward=True, norm_cost=True),
+                     "nocost": dict(norm_obs=True, norm_reward=True, norm_cost=False),
+                     "raw": dict(norm_obs=False, norm_reward=False, norm_cost=False)}.items():
+        env = DummyVecEnv([(lambda i=i: ScriptedEnv(100 + i)) for i in range(n_envs)])
+        env = VecCostWrapper(env)
+        env = VecNormalizeWithCost(env, training=True, cost_info_str="cost", reward_gamma=0.99, cost_gamma=0.97, **kw)
+        env.set_cost_function(scripted_cost)
+        acts = scripted_actions(7, steps, n_envs)
+        out = dict(obs0=env.reset(), obs=[], orig_obs=[], rew=[], done=[], cost=[], orig_cost=[])
+        for t in range(steps):
+            o, r, d, infos = env.step(acts[t])
+            out["obs"].append(o), out["orig_obs"].append(env.get_original_obs()), out["rew"].append(r)
+            out["done"].append(d), out["cost"].append([i["cost"] for i in infos])
+            out["orig_cost"].append(env.get_original_cost())
+        arrays = {k: np.asarray(v) for k, v in out.items()}
+        for rms in ("obs_rms", "ret_rms", "cost_rms"):
+            r = getattr(env, rms)
+            arrays[rms + "_mean"], arrays[rms + "_var"], arrays[rms + "_count"] = r.mean, r.var, np.float64(r.count)
+        # eval env synced from the training env: normalised obs of a fresh episode
+        ev = VecNormalizeWithCost(DummyVecEnv([lambda: ScriptedEnv(555)]), training=False, norm_obs=kw["norm_obs"],
+                                  norm_reward=False, norm_cost=False)
+        sync_envs_normalization(env, ev)
+        arrays["eval_obs0"] = ev.reset()
+        arrays["eval_obs1"] = ev.step(acts[0][:1])[0]
+        save(f"venv_{name}", **arrays)
+
+
+# ------------------------------------------------------------------------------------------- CLI flag surface
+def golden_flags():
+    """The reference drivers' argparse surface, read from their source with `ast` (they import wandb / MuJoCo envs
+    and cannot be executed here): option strings, action, nargs and literal defaults -> tests/golden/flags_*.json."""
+    import ast
+    import json
+    for name, rel in {"icrl": "icrl/icrl.py", "cpg": "icrl/cpg.py", "run_policy": "icrl/run_policy.py"}.items():
+        tree = ast.parse(open(os.path.join(REF, rel)).read())
+        flags = []
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Call) and getattr(node.func, "attr", "") == "add_argument":
+                opts = [a.value for a in node.args]
+                kw = {}
+                for k in node.keywords:
+                    if k.arg in ("default", "action", "nargs"):
+                        kw[k.arg] = ast.literal_eval(k.value)
+                    elif k.arg == "type":
+                        kw["type"] = ast.unparse(k.value)
+                flags.append(dict(opts=opts, **kw))
+        with open(os.path.join(OUT, f"flags_{name}.json"), "w") as f:
+            json.dump(flags, f, indent=1)
+        print(f"wrote flags_{name}.json ({len(flags)} flags)")
+
+
+# ------------------------------------------------------------------------------------------- reference checkpoints
+def golden_ckpt():
+    """Copy two of the reference's expert `best_model.zip` DATA files (SB3 zip checkpoints, not source) and record what
+    the reference's own `PPOLagrangian.load(...).policy.evaluate_actions` returns for seeded inputs."""
+    import shutil
+    for name, sub, disc in (("lgw", "LGW", True), ("hc", "HCWithPos-New", False)):
+        src = os.path.join(REF, "icrl/expert_data", sub, "files/best_model.zip")
+        dst = os.path.join(OUT, f"ref_{name}_best_model.zip")
+        shutil.copyfile(src, dst)
+        os.chmod(dst, 0o644)
+        # the zip's `data` cloudpickles real gym spaces (not importable here), so the reference policy is built on
+        # a stub env of the same shape and the zip's tensors are loaded into it with the reference's own classes
+        import io
+        import zipfile
+        zf = zipfile.ZipFile(src)
+        sd = th.load(io.BytesIO(zf.read("policy.pth")), map_location="cpu", weights_only=False)
+        osd = th.load(io.BytesIO(zf.read("policy.optimizer.pth")), map_location="cpu", weights_only=False)
+        obs_dim, act_out = sd["mlp_extractor.policy_net.0.weight"].shape[1], sd["action_net.weight"].shape[0]
+        env = DummyVecEnv([lambda: FakeEnv(obs_dim, act_out, disc)])
+        model = PPOLagrangian("TwoCriticsMlpPolicy", env, device="cpu")
+        model.policy.load_state_dict(sd)
+        pol = model.policy
+        rng = np.random.default_rng(11)
+        obs = rng.standard_normal((64, obs_dim)).astype(np.float32) * 2
+        acts = (rng.integers(0, 2, (64,)).astype(np.float32) if disc
+                else rng.uniform(-1, 1, (64, act_out)).astype(np.float32))
+        with th.no_grad():
+            v, cv, lp, ent = pol.evaluate_actions(th.tensor(obs), th.tensor(acts))
+        save(f"ckpt_{name}", obs=obs, acts=acts, values=v.numpy(), cost_values=cv.numpy(), log_prob=lp.numpy(),
+             entropy=ent.numpy(), adam_m0=osd["state"][osd["param_groups"][0]["params"][0]]["exp_avg"].numpy(),
+             adam_step=np.int64(osd["state"][osd["param_groups"][0]["params"][0]]["step"]))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["k1", "k2", "k3", "k4"]
     for w in which:
