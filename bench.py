@@ -122,7 +122,7 @@ def cpu_iteration_estimate(w, k4_steps, seed=0):
     rollout, K4 `k4_steps` optimiser steps of one rollout, K2 the full `backward_iters` (per-step IS via the O(N)
     identity, i.e. *cheaper* than the reference's N x N broadcast)."""
     from icrl_b200.learner import synth_demos, synth_rollouts
-    from oracle import cn as ocn, gae as ogae, ppo as oppo
+    from oracle import cn as ocn, costnorm, gae as ogae, ppo as oppo
     th.manual_seed(seed)
     T, E, n = w.n_steps, w.n_envs, w.n_steps * w.n_envs
     small = type(w)(**{**w.__dict__, "rollouts": 1})
@@ -143,8 +143,12 @@ def cpu_iteration_estimate(w, k4_steps, seed=0):
     oo, aa = host["orig_obs"][0].astype(np.float64), host["actions"][0]
     t0 = time.perf_counter()
     costs = np.zeros((T, E), np.float32)
+    news = np.concatenate([host["dones"][0][1:], host["last_dones"][0][None].astype(np.float32)]) != 0
+    cstate = costnorm.reset(costnorm.initial_state(E))
     for s in range(calls):
         costs[s] = ocn.cost_function(cn_params, spec, oo[s], aa[s])
+        if w.normalize_cost:      # VecNormalizeWithCost.step_wait, per env step as the reference runs it
+            costs[s] = costnorm.normalize_rollout(costs[s:s + 1], news[s:s + 1], cstate)[0]
     t["k1"] = (time.perf_counter() - t0) / calls * T
     costs = np.tile(costs[:calls], (T // calls + 1, 1))[:T].copy()
     # K3
@@ -251,6 +255,13 @@ class HostLearner:
             self.pristine.append({k: getattr(b, k) for k in ("observations", "orig_observations", "actions", "log_probs",
                                                               "reward_values", "cost_values")})
         self.last_dones = host["last_dones"]
+        # the cost statistics a VecNormalizeWithCost would carry (state after reset())
+        import types
+        from icrl_b200.vec_env import RunningMeanStd
+        rms = RunningMeanStd(shape=())
+        rms.update(np.zeros(E))
+        self.vn = types.SimpleNamespace(cost_rms=rms, cost_ret=np.zeros(E), cost_gamma=0.99, epsilon=1e-8, clip_cost=10.0,
+                                        norm_cost=True, training=True, old_cost=None)
         if w.nominal_rows:
             from icrl_b200.learner import synth_demos
             _, _, self.no, self.na, self.lengths = synth_demos(w, 0)
@@ -263,9 +274,14 @@ class HostLearner:
             for k, arr in self.pristine[r].items():   # "freshly collected" time-major arrays (train() rebinds env-major copies)
                 setattr(b, k, arr)
             b.generator_ready = False
-            costs = self.cn.cost_function(b.orig_observations, b.actions)                      # K1
-            b.costs[:], b.orig_costs[:] = costs, costs
-            h2d += b.orig_observations.nbytes + b.actions.nbytes; d2h += costs.nbytes
+            if w.normalize_cost:                                                               # K1 + K5
+                b.relabel_costs(self.cn, self.vn, self.last_dones[r])
+                h2d += b.orig_observations.nbytes + b.actions.nbytes + b.dones.nbytes + b.n_envs + (3 + b.n_envs) * 8
+                d2h += 2 * b.costs.nbytes + (3 + b.n_envs) * 8
+            else:
+                costs = self.cn.cost_function(b.orig_observations, b.actions)                  # K1
+                b.costs[:], b.orig_costs[:] = costs, costs
+                h2d += b.orig_observations.nbytes + b.actions.nbytes; d2h += costs.nbytes
             b.compute_returns_and_advantage(b.reward_values[-1], b.cost_values[-1], self.last_dones[r])   # K3
             h2d += 5 * n * 4 + 2 * b.n_envs * 4 + b.n_envs; d2h += 4 * n * 4
             self.algo.rollout_buffer = b
@@ -363,6 +379,13 @@ def family_rooflines(learner, peak):
         d = timeit(lambda: _lib.check(L.icrl_dual_gae(*[_lib.ptr(x) for x in arrs + lv], T, E, 0.99, 0.95, 0.99, 0.95,
                                                       *[_lib.ptr(o) for o in outs], _lib.current_stream())))
         out[f"k3_{tag}"] = {"rows": n, "us": d * 1e6, "GB/s": 36 * n / d / 1e9, "frac_hbm": 36 * n / d / 1e9 / peak}
+        if tag == "rollout":
+            # K5: T-serial float64 statistics chain (bit-exact with numpy) -- latency-bound, not a bandwidth kernel
+            state = th.tensor([0.0, 1.0, 1e-4] + [0.0] * E, dtype=th.float64, device=learner.dev)
+            d = timeit(lambda: _lib.check(L.icrl_cost_normalize(_lib.ptr(arrs[0]), _lib.ptr(arrs[4]), _lib.ptr(lv[2]), T, E,
+                                                                0.99, 1e-8, 10.0, 1, 1, _lib.ptr(state), _lib.ptr(outs[0]),
+                                                                _lib.current_stream())))
+            out["k5_rollout"] = {"rows": n, "us": d * 1e6, "GB/s": 13 * n / d / 1e9, "frac_hbm": 13 * n / d / 1e9 / peak}
     return out
 
 

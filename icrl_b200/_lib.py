@@ -96,6 +96,8 @@ SIGNATURES = {
     "icrl_comm_free": (C.c_int, [c_void]),
     "icrl_policy_forward": (C.c_int, [C.POINTER(PpoCfg), c_void, c_void, C.c_int64, c_void, c_void, c_void, c_void]),
     "icrl_dual_update": (C.c_int, [c_void, c_void, C.c_int64, C.c_double, C.c_double, C.c_int64, C.c_double, c_void]),
+    "icrl_cost_normalize": (C.c_int, [c_void, c_void, c_void, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
+                                      C.c_int32, C.c_int32, c_void, c_void, c_void]),
 }
 
 

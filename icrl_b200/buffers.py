@@ -17,7 +17,7 @@ import torch as th
 
 from . import _lib
 from .device import resolve_device
-from .spaces import get_action_dim, get_obs_shape
+from .spaces import get_action_dim, get_obs_shape, is_discrete
 from .type_aliases import RolloutBufferWithCostSamples
 
 _FLAT_FIELDS = ["orig_observations", "observations", "actions", "log_probs", "reward_values", "reward_advantages",
@@ -99,6 +99,45 @@ class RolloutBufferWithCost:
                 float(self.reward_gamma), float(self.reward_gae_lambda), float(self.cost_gamma),
                 float(self.cost_gae_lambda), *[_lib.ptr(o) for o in outs], _lib.current_stream()))
         self.reward_advantages, self.reward_returns, self.cost_advantages, self.cost_returns = outs
+
+    # ---------------------------------------------------------------- K1 + K5 on the whole rollout
+    def relabel_costs(self, constraint_net, cost_normalizer, last_dones: np.ndarray) -> None:
+        """Fill `orig_costs` / `costs` for the whole rollout after collection, instead of one cost_function call per
+        environment step: K1 over [T*E] rows of (orig_observations, actions), then the online statistics of
+        `cost_normalizer` (a VecNormalizeWithCost, or None) replayed on the device by icrl_cost_normalize -- bit-exact
+        with what vec_cost_wrapper.py:37-41 + vec_normalize.py:232-257 would have produced step by step, because the
+        constraint net does not change during collection."""
+        T, E = self.buffer_size, self.n_envs
+        dev = self._device()
+        with th.cuda.device(dev):
+            obs = th.from_numpy(np.ascontiguousarray(self.orig_observations)).to(dev).reshape(T * E, -1)
+            acs = self.actions
+            if not is_discrete(self.action_space):      # the environment (and so the cost wrapper) saw clipped actions
+                acs = np.clip(acs, self.action_space.low, self.action_space.high)
+            acs = th.from_numpy(np.ascontiguousarray(acs, dtype=np.float32)).to(dev).reshape(T * E, -1)
+            if is_discrete(self.action_space):
+                acs = acs.reshape(-1)
+            orig = constraint_net.cost_function_device(obs, acs).reshape(T, E)
+            costs = orig
+            vn = cost_normalizer
+            if vn is not None:
+                state = np.concatenate([[vn.cost_rms.mean, vn.cost_rms.var, vn.cost_rms.count], vn.cost_ret]).astype(np.float64)
+                state_d = th.from_numpy(state).to(dev)
+                dones_d = th.from_numpy(np.ascontiguousarray(self.dones)).to(dev)
+                last_d = th.from_numpy(np.ascontiguousarray(np.asarray(last_dones).astype(np.uint8).reshape(-1))).to(dev)
+                costs = th.empty_like(orig)
+                _lib.check(_lib.lib().icrl_cost_normalize(
+                    _lib.ptr(orig), _lib.ptr(dones_d), _lib.ptr(last_d), T, E, float(vn.cost_gamma), float(vn.epsilon),
+                    float(vn.clip_cost), int(bool(vn.norm_cost)), int(bool(vn.training)), _lib.ptr(state_d),
+                    _lib.ptr(costs), _lib.current_stream()))
+                state = state_d.cpu().numpy()
+                if vn.training:
+                    vn.cost_rms.mean, vn.cost_rms.var, vn.cost_rms.count = state[0], state[1], float(state[2])
+                    vn.cost_ret = state[3:].copy()
+            self.orig_costs = orig.cpu().numpy()
+            self.costs = self.orig_costs if costs is orig else costs.cpu().numpy()
+            if vn is not None:
+                vn.old_cost = self.orig_costs[-1].copy()
 
     def _device(self):
         if self._dev is None:

@@ -209,8 +209,8 @@ class ConstraintNet:
         d.clip_obs = float(self.clip_obs) if self.clip_obs is not None else 0.0
         d.has_clip_acs = int(self.action_high is not None and self.action_low is not None and not self.is_discrete)
         if d.has_clip_acs:
-            low = np.broadcast_to(np.asarray(self.action_low, dtype=np.float32), (self.acs_dim,))
-            high = np.broadcast_to(np.asarray(self.action_high, dtype=np.float32), (self.acs_dim,))
+            low = np.broadcast_to(np.asarray(self.action_low, dtype=np.float32), (self.acs_dim,)).copy()
+            high = np.broadcast_to(np.asarray(self.action_high, dtype=np.float32), (self.acs_dim,)).copy()
             self._low_dev = th.from_numpy(np.ascontiguousarray(low)).to(self._dev)
             self._high_dev = th.from_numpy(np.ascontiguousarray(high)).to(self._dev)
             d.acs_low, d.acs_high = self._low_dev.data_ptr(), self._high_dev.data_ptr()

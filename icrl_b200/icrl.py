@@ -67,7 +67,10 @@ def icrl(config):
         action_low=action_low, action_high=action_high, target_kl_old_new=config.cn_target_kl_old_new,
         target_kl_new_old=config.cn_target_kl_new_old, train_gail_lambda=config.train_gail_lambda, eps=config.cn_eps,
         device=config.device)
-    train_env.set_cost_function(constraint_net.cost_function)
+    # ICRL_WHOLE_BUFFER_RELABEL=1: relabel + cost-normalise each rollout on the device after collection instead of
+    # calling the cost function at every environment step (same numbers, T fewer launches per rollout)
+    whole_buffer = os.environ.get("ICRL_WHOLE_BUFFER_RELABEL", "0") == "1"
+    train_env.set_cost_function(None if whole_buffer else constraint_net.cost_function)
     true_cost_function = get_true_cost_function(config.eval_env_id)
 
     create_nominal_agent = lambda: PPOLagrangian(
@@ -109,7 +112,8 @@ def icrl(config):
         current_progress_remaining = 1 - float(itr) / float(config.n_iters)
 
         # forward step: PPO-Lagrangian on the current constraint (K1 per env step, K3 + K4 per rollout)
-        nominal_agent.learn(total_timesteps=config.forward_timesteps, cost_function="cost")
+        nominal_agent.learn(total_timesteps=config.forward_timesteps,
+                            cost_function=constraint_net if whole_buffer else "cost")
         forward_metrics = dict(logger.Logger.CURRENT.name_to_value)
         timesteps += nominal_agent.num_timesteps
 
@@ -123,7 +127,7 @@ def icrl(config):
             mean, var = sampling_env.obs_rms.mean, sampling_env.obs_rms.var
         backward_metrics = constraint_net.train(config.backward_iters, orig_observations, actions, lengths, mean, var,
                                                 current_progress_remaining)
-        train_env.set_cost_function(constraint_net.cost_function)
+        train_env.set_cost_function(None if whole_buffer else constraint_net.cost_function)
 
         average_true_cost = np.mean(true_cost_function(orig_observations, actions))
         samples_behind = np.mean(orig_observations[..., 0] < -3)

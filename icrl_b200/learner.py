@@ -18,6 +18,7 @@ from .constraint_net import ConstraintNet
 from .device import resolve_device
 from .dual_variable import DualVariable
 from .policies import ActorTwoCriticsPolicy
+from .vec_env import RunningMeanStd
 from .spaces import Box, Discrete
 
 
@@ -48,6 +49,7 @@ class Workload:
     penalty_initial_value: float = 1.0
     penalty_learning_rate: float = 0.1
     clip_obs: float = 20.0
+    normalize_cost: bool = True    # VecNormalizeWithCost cost stream (off with -dnc)
 
     @property
     def transitions_per_iteration(self) -> int:
@@ -57,7 +59,8 @@ class Workload:
 WORKLOADS = {
     # python run_me.py icrl ... -tei LGW-v0 -cl 20 -clr 0.003 -ft 0.5e5 -ni 10 -bi 20 -dno -dnr -dnc   (README.md:25)
     "lapgrid": Workload("LapGrid LGW-v0 ICRL (cl 20, ft 5e4, bi 20)", 1, 2, True, (20,), rollouts=5, backward_iters=20,
-                        expert_rows=4000, nominal_rows=4000, episode_len=200, per_step_is=False, cn_reg=0.0, cn_lr=0.003),
+                        expert_rows=4000, nominal_rows=4000, episode_len=200, per_step_is=False, cn_reg=0.0, cn_lr=0.003,
+                        normalize_cost=False),
     # ... -tei HCWithPos-v0 -cl 20 -bi 10 -ft 2e5 -clr 0.05 -crc 0.5 -psis                              (README.md:38)
     "halfcheetah": Workload("HalfCheetah HCWithPos-v0 ICRL (cl 20, ft 2e5, bi 10)", 18, 6, False, (20,)),
     # ... -tei AntWall-v0 -cl 40 40 -clr 0.005 -crc 0.6 -bi 5 -ft 2e5 --batch_size 128 --n_epochs 20 ... (README.md:50)
@@ -152,6 +155,11 @@ class DeviceLearner:
         self.reward_values, self.cost_values, self.log_probs = z(R, T, E), z(R, T, E), z(R, T, E)
         self.last_rv, self.last_cv = z(R, E), z(R, E)
         self.costs = z(R, T, E)
+        # K5: VecNormalizeWithCost's cost statistics {mean, var, count, cost_ret[E]} as they stand after reset()
+        self.costs_norm = z(R, T, E) if w.normalize_cost else self.costs
+        rms = RunningMeanStd(shape=())
+        rms.update(np.zeros(E))
+        self.cost_state = th.tensor([rms.mean, rms.var, rms.count] + [0.0] * E, dtype=th.float64, device=d)
         self.adv_r, self.ret_r, self.adv_c, self.ret_c = z(R, T, E), z(R, T, E), z(R, T, E), z(R, T, E)
         self.steps_per_epoch = (self.n + w.batch_size - 1) // w.batch_size
         self.stats = z(R, w.n_epochs * self.steps_per_epoch, _lib.PPO_STATS_PER_STEP)
@@ -211,9 +219,14 @@ class DeviceLearner:
             # K1: relabel the whole rollout with the current constraint net (VecCostWrapper.step_wait, batched)
             _lib.check(L.icrl_cn_forward(C.byref(desc), _lib.ptr(self.data["orig_obs"][r]), 0,
                                          _lib.ptr(self.data["actions"][r]), self.n, _lib.ptr(self.costs[r]), 0, st))
+            # K5: the cost stream of VecNormalizeWithCost replayed over the whole rollout (float64 statistics on device)
+            if w.normalize_cost:
+                _lib.check(L.icrl_cost_normalize(_lib.ptr(self.costs[r]), _lib.ptr(self.data["dones"][r]),
+                                                 _lib.ptr(self.data["last_dones"][r]), w.n_steps, self.E, 0.99, 1e-8, 10.0,
+                                                 1, 1, _lib.ptr(self.cost_state), _lib.ptr(self.costs_norm[r]), st))
             # K3: dual GAE
             _lib.check(L.icrl_dual_gae(
-                _lib.ptr(self.data["rewards"][r]), _lib.ptr(self.reward_values[r]), _lib.ptr(self.costs[r]),
+                _lib.ptr(self.data["rewards"][r]), _lib.ptr(self.reward_values[r]), _lib.ptr(self.costs_norm[r]),
                 _lib.ptr(self.cost_values[r]), _lib.ptr(self.data["dones"][r]), _lib.ptr(self.last_rv[r]),
                 _lib.ptr(self.last_cv[r]), _lib.ptr(self.data["last_dones"][r]), w.n_steps, self.E, 0.99,
                 w.reward_gae_lambda, 0.99, w.cost_gae_lambda, _lib.ptr(self.adv_r[r]), _lib.ptr(self.ret_r[r]),

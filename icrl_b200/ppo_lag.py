@@ -62,6 +62,16 @@ class _CallbackList(_NullCallback):
     def on_training_end(self): [c.on_training_end() for c in self.callbacks]
 
 
+def _find_cost_normalizer(env):
+    """The VecNormalizeWithCost layer of a wrapped env (None when costs are not normalised)."""
+    from .vec_env import VecEnvWrapper, VecNormalizeWithCost
+    while isinstance(env, VecEnvWrapper):
+        if isinstance(env, VecNormalizeWithCost):
+            return env
+        env = env.venv
+    return None
+
+
 class PPOLagrangian:
     def __init__(
         self,
@@ -324,6 +334,9 @@ class PPOLagrangian:
         callback.on_rollout_start()
         has_orig_obs = hasattr(env, "get_original_obs")
         discrete = _is_discrete(self.action_space)
+        # whole-buffer mode: `cost_function` is the ConstraintNet itself -> no per-step cost calls, the
+        # rollout is relabelled (K1) and cost-normalised (K5) on the device once collection is over
+        relabel = hasattr(cost_function, "cost_function_device")
         while n_steps < n_rollout_steps:
             actions, reward_values, cost_values, log_probs = self.policy.forward(th.as_tensor(np.asarray(self._last_obs)))
             actions = actions.numpy()
@@ -332,7 +345,9 @@ class PPOLagrangian:
                 clipped_actions = np.clip(actions, self.action_space.low, self.action_space.high)
             new_obs, rewards, dones, infos = env.step(clipped_actions)
             orig_obs = env.get_original_obs() if has_orig_obs else new_obs
-            if type(cost_function) is str:
+            if relabel:
+                costs = orig_costs = np.zeros(env.num_envs, dtype=np.float32)      # filled for the whole buffer below
+            elif type(cost_function) is str:
                 costs = np.array([info.get(cost_function, 0) for info in infos])
                 orig_costs = env.get_original_cost() if hasattr(env, "get_original_cost") else costs
             else:
@@ -348,6 +363,8 @@ class PPOLagrangian:
             rollout_buffer.add(self._last_obs, self._last_original_obs, new_obs, orig_obs, actions, rewards, costs,
                                orig_costs, self._last_dones, reward_values, cost_values, log_probs)
             self._last_obs, self._last_original_obs, self._last_dones = new_obs, orig_obs, dones
+        if relabel:
+            rollout_buffer.relabel_costs(cost_function, _find_cost_normalizer(env), dones)
         rollout_buffer.compute_returns_and_advantage(reward_values, cost_values, dones=dones)
         callback.on_rollout_end()
         return True

@@ -243,6 +243,21 @@ int icrl_policy_forward(const icrl_ppo_cfg* cfg, const float* params, const floa
 int icrl_dual_update(float* state, const float* orig_costs, int64_t n, double alpha, double lr, int64_t adam_step_before,
                      double clamp_min_log_nu, void* stream);
 
+/* Whole-rollout cost normalisation -- replaces, for a [T, E] rollout relabelled by icrl_cn_forward,
+ * the T per-step host updates of VecNormalizeWithCost.step_wait / _update_cost / normalize_cost
+ * (stable_baselines3/common/vec_env/vec_normalize.py:232-257) and RunningMeanStd.update
+ * (stable_baselines3/common/running_mean_std.py:19-39).  All device pointers.
+ *   orig_costs [T, E] float32   what the cost function returned at each step
+ *   dones      [T, E] float32   buffer layout: dones[t] = episode ended at step t-1 (buffers.py add());
+ *   last_dones [E]    uint8     episode ended at step T-1            -> `news` of step t = dones[t+1] / last_dones
+ *   state      float64 [3 + E]  {cost_rms.mean, cost_rms.var, cost_rms.count, cost_ret[E]}, read and updated when
+ *                               `training` (bit-exact with the numpy float64 arithmetic, pairwise sums included)
+ *   costs      [T, E] float32   clip(orig / sqrt(var_after_step_t + epsilon), +-clip_cost) when `norm_cost`, else a copy
+ * (may alias orig_costs). */
+int icrl_cost_normalize(const float* orig_costs, const float* dones, const uint8_t* last_dones, int32_t T, int32_t E,
+                        double cost_gamma, double epsilon, double clip_cost, int32_t norm_cost, int32_t training,
+                        double* state, float* costs, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

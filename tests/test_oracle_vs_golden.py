@@ -168,3 +168,16 @@ def test_k4_train_matches_reference(case):
                    "train/approx_kl": out["last_epoch_approx_kl"], "train/early_stop_epoch": out["early_stop_epoch"]}
             for k, v in chk.items():
                 assert abs(v - log[k]) <= 1e-5 * max(abs(log[k]), 1e-2), (k, v, log[k])
+
+
+# ------------------------------------------------------------------------------------------- cost normalisation (f1)
+@pytest.mark.parametrize("name,norm", [("all", True), ("nocost", False)])
+def test_costnorm_oracle_matches_reference_wrappers(name, norm):
+    from oracle import costnorm
+    g = load_golden(f"venv_{name}")
+    T, E = g["orig_cost"].shape
+    state = costnorm.reset(costnorm.initial_state(E))
+    out = costnorm.normalize_rollout(g["orig_cost"], g["done"], state, cost_gamma=0.97, norm_cost=norm)
+    np.testing.assert_array_equal(out, g["cost"].astype(np.float32))
+    assert state["mean"] == g["cost_rms_mean"] and state["var"] == g["cost_rms_var"]
+    assert state["count"] == float(g["cost_rms_count"])
