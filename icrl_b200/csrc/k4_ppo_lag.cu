@@ -22,6 +22,8 @@
 //     tcgen05 is not used here on purpose: M=64 tiles on a dependent chain of five tiny GEMMs would pay a TMEM
 //     allocate / commit / mbarrier / tcgen05.ld round trip per layer, and the epilogues (tanh, derivative masks, Adam)
 //     want the accumulators in registers.
+#include <type_traits>
+
 #include "k4_common.cuh"
 
 namespace icrl {
@@ -874,8 +876,123 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                     g_s += x.x; tot[0] += x.y; tot[1] += x.z; tot[2] += x.w; tot[3] += y.x; tot[4] += y.y;
                 }
                 // ---- (3) data parallel: all-reduce the pair sums across the ranks' matching CTAs over NVLink peer memory
+                bool exchanged = false;
                 if (DIST && a.world > 1) {
-                    // "LL" protocol (as NCCL's low-latency path): every 16-byte store carries two values and two copies of
+                    // ---- (3a) 4 / 8 ranks: reduce-scatter + all-gather, both with self-validating words.
+                    // The direct scheme below makes every thread read W full gradient copies one after the other (W x 2
+                    // dependent L2 round trips, which is what made the exchange cost grow linearly with W).  Here the
+                    // F floats a thread owns are cut into W slices; rank q sums slice q of every rank IN RANK ORDER (so all
+                    // replicas see the same bits), then broadcasts the sum.  Per thread: W*NWD words in, W*NWD words out,
+                    // each phase polled in one or two batches -> two NVLink hops, cost independent of W.  A word is
+                    // {f0, f1, f2, seq ^ hash(f0, f1, f2)}: three payload floats ride with one self-validating tag, and a
+                    // torn 16-byte store cannot pass for a whole one.  The two CTAs of
+                    // a pair hold identical sums: half h sends only to the ranks of parity h, both poll the same slabs.
+                    const unsigned int want = a.flag_base + (unsigned int)step + 1u;
+                    constexpr int F = NTW2 * 4 + NT1 * 4 + 4 + 1 + 5;       // gradient floats + loss sums owned by a thread
+                    auto G = [&](int k) -> float& {                           // k is a compile-time constant at every use
+                        if (k < NTW2 * 4) return g_w2[k >> 2][k & 3];
+                        k -= NTW2 * 4;
+                        if (k < NT1 * 4) return g_w1[k >> 2][k & 3];
+                        k -= NT1 * 4;
+                        if (k < 4) return g_hw[k];
+                        k -= 4;
+                        if (k == 0) return g_s;
+                        return tot[k - 1];
+                    };
+                    auto rsag = [&](auto wc) {
+                        constexpr int W = decltype(wc)::value;
+                        constexpr int S = (F + W - 1) / W;                  // floats per slice
+                        constexpr int NWD = (S + 2) / 3;                    // words per slice
+                        static_assert(NWD <= RSAG_MAXW, "RS/AG slab too small");
+                        const int me = a.rank;
+                        auto slab = [&](float* base, int region, int src) {
+                            return reinterpret_cast<uint4*>(base) +
+                                   ((((size_t)(region * 2 + parity) * ICRL_PPO_MAX_RANKS + src) * 3 + role) * RSAG_MAXW) * NTT + tid;
+                        };
+                        // the fourth lane is the sequence number XOR a hash of the payload: a word that arrived torn (old and
+                        // new 8-byte halves mixed) fails the check unless the mixed-in old half equals the new one anyway
+                        auto tag = [&](unsigned int x, unsigned int y, unsigned int z) {
+                            return want ^ ((x ^ __funnelshift_l(y, y, 11) ^ __funnelshift_l(z, z, 22)) * 0x9E3779B1u);
+                        };
+                        auto put = [&](uint4* dst, int j, float x, float y, float z) {
+                            const unsigned int xi = __float_as_uint(x), yi = __float_as_uint(y), zi = __float_as_uint(z);
+                            dst[j * NTT] = make_uint4(xi, yi, zi, tag(xi, yi, zi));
+                        };
+                        // polls NW words (word w -> slab(region, w / NWD) + (w % NWD) * NTT), 16 per round trip, and hands
+                        // each validated word to `sink(w, x, y, z)`
+                        const long long tstart = clock64();
+                        auto poll = [&](int region, auto sink) {
+                            constexpr int NW = W * NWD;
+#pragma unroll
+                            for (int w0 = 0; w0 < NW; w0 += 16) {
+                                uint4 x[16];
+                                for (;;) {
+                                    bool ok = true;
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j)
+                                        if (w0 + j < NW) {
+                                            const uint4* src = slab(a.recv[me], region, (w0 + j) / NWD) + ((w0 + j) % NWD) * NTT;
+                                            asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                                         : "=r"(x[j].x), "=r"(x[j].y), "=r"(x[j].z), "=r"(x[j].w)
+                                                         : "l"(src) : "memory");
+                                        }
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j)
+                                        if (w0 + j < NW) ok = ok && (x[j].w == tag(x[j].x, x[j].y, x[j].z));
+                                    if (ok) break;
+                                    if (clock64() - tstart > 4000000000LL) { XCH[31] = 1.f; break; }   // ~2 s: a peer is gone
+                                }
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    if (w0 + j < NW)
+                                        sink(w0 + j, __uint_as_float(x[j].x), __uint_as_float(x[j].y), __uint_as_float(x[j].z));
+                            }
+                        };
+                        // reduce-scatter: slice q of my floats -> rank q
+#pragma unroll
+                        for (int q = 0; q < W; ++q) {
+                            if ((q & 1) != half) continue;
+                            uint4* dst = slab(a.recv[q], 0, me);
+#pragma unroll
+                            for (int j = 0; j < NWD; ++j) {
+                                const int k = q * S + 3 * j;
+                                put(dst, j, (3 * j < S && k < F) ? G(k) : 0.f, (3 * j + 1 < S && k + 1 < F) ? G(k + 1) : 0.f,
+                                    (3 * j + 2 < S && k + 2 < F) ? G(k + 2) : 0.f);
+                            }
+                        }
+                        float red[S];
+#pragma unroll
+                        for (int i = 0; i < S; ++i) red[i] = 0.f;
+                        poll(0, [&](int w, float x, float y, float z) {       // w ascending == rank ascending per element
+                            const int i = 3 * (w % NWD);
+                            if (i < S) red[i] += x;
+                            if (i + 1 < S) red[i + 1] += y;
+                            if (i + 2 < S) red[i + 2] += z;
+                        });
+                        // all-gather: my reduced slice -> every rank
+#pragma unroll
+                        for (int pr = 0; pr < W; ++pr) {
+                            if ((pr & 1) != half) continue;
+                            uint4* dst = slab(a.recv[pr], 1, me);
+#pragma unroll
+                            for (int j = 0; j < NWD; ++j)
+                                put(dst, j, (3 * j < S) ? red[3 * j] : 0.f, (3 * j + 1 < S) ? red[3 * j + 1] : 0.f,
+                                    (3 * j + 2 < S) ? red[3 * j + 2] : 0.f);
+                        }
+                        poll(1, [&](int w, float x, float y, float z) {
+                            const int q = w / NWD, i = 3 * (w % NWD), k = q * S + i;
+                            if (i < S && k < F) G(k) = x;
+                            if (i + 1 < S && k + 1 < F) G(k + 1) = y;
+                            if (i + 2 < S && k + 2 < F) G(k + 2) = z;
+                        });
+                    };
+                    const bool want_rsag = a.dist_mode == 2 || (a.dist_mode == 0 && a.world >= 4);
+                    if (want_rsag && a.world == 8) { rsag(std::integral_constant<int, 8>{}); exchanged = true; }
+                    else if (want_rsag && a.world == 4) { rsag(std::integral_constant<int, 4>{}); exchanged = true; }
+                    else if (want_rsag && a.world == 2) { rsag(std::integral_constant<int, 2>{}); exchanged = true; }
+                }
+                if (DIST && a.world > 1 && !exchanged) {
+                    // ---- (3b) any other world size: direct exchange.  "LL" protocol (as NCCL's low-latency path): every 16-byte store carries two values and two copies of
                     // this step's sequence number, so the data validates itself -- no fence, no separate flag, no barrier:
                     // the exchange costs one NVLink store latency.  (A torn 16-byte store is still two self-validating
                     // 8-byte halves.)  Buffers alternate by step parity and the sequence number grows monotonically, so a
@@ -1193,6 +1310,10 @@ static int ppo_train_impl(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, fl
     a.params = params; a.adam_m = adam_m; a.adam_v = adam_v; a.stats = step_stats; a.result = result;
     a.step_before = adam_step_before;
     if (a.world < 1) { a.world = 1; a.rank = 0; }
+    {
+        const char* m = getenv("ICRL_PPO_DIST_MODE");      // 0 auto, 1 direct exchange, 2 reduce-scatter/all-gather
+        a.dist_mode = m ? atoi(m) : 0;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     {
         const int total_steps = a.n_epochs * a.steps_per_epoch;
