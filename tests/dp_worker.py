@@ -25,6 +25,8 @@ def main():
     from oracle import cn as ocn, gae as ogae, ppo as oppo
 
     D, A, T, E_local, B_local, n_epochs = 18, 6, 32, 2, 32, 3
+    if os.environ.get("ICRL_DP_TEST_SHAPE") == "ant":      # the widest layer-1 tiling (NT1 = 8) through the exchange
+        D, A = 113, 8
     E = E_local * world
     rng = np.random.default_rng(7)                       # identical global data on every rank
     g = {"observations": rng.standard_normal((T, E, D)).astype(np.float32),
