@@ -308,6 +308,14 @@ def time_steps(fn, steps, world, flush):
     return max_over_ranks(sum(s.elapsed_time(e) for s, e in evs) * 1e-3, world)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE full K4 launch, from the `ncu --set full` captures summarised in
+# profiles/SUMMARY_r01.md (gpurun_out/k4_r01.ncu-rep, k4_ant_r01.ncu-rep); keyed by Workload.name
+K4_NCU_TRAFFIC_BYTES = {
+    "HalfCheetah HCWithPos-v0 ICRL (cl 20, ft 2e5, bi 10)": 21652480,
+    "AntWall-v0 ICRL (cl 40 40, ft 2e5, bi 5, batch 128, n_epochs 20)": 122238720 + 3342848,
+}
+
+
 def kernel_roofline(learner, peak, peak_src):
     """Dominant kernel = the persistent K4 launch: CUDA events around each of R launches on the launching stream."""
     import ctypes as C
@@ -337,8 +345,9 @@ def kernel_roofline(learner, peak, peak_src):
     bytes_per_pass = (w.obs_dim + (1 if w.is_discrete else w.act_dim) + 7) * 4
     alg_bytes = bytes_per_pass * learner.n * w.n_epochs
     achieved = alg_bytes / dur / 1e9
-    return {"bound": "hbm", "kernel": "ppo_train_kernel (K4, persistent 3-CTA cluster)", "achieved": achieved, "peak": peak,
-            "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+    return {"bound": "hbm", "kernel": "ppo_train_kernel (K4, persistent 6-CTA cluster: a CTA pair per trunk)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": K4_NCU_TRAFFIC_BYTES.get(learner.w.name), "peak_source": peak_src,
             "launch_ms": dur * 1e3, "optimiser_steps_per_launch": steps, "us_per_optimiser_step": dur / steps * 1e6,
             "algorithmic_bytes_per_launch": alg_bytes,
             "note": "1600 dependent optimiser steps on 64-128 rows each: latency-bound by construction (SURVEY §7), "
