@@ -132,7 +132,7 @@ __host__ __device__ inline PpoSmem ppo_smem_layout(int LDX, int NP) {
     s.dmean = o; o += RBH * AMAX;
     s.act = o; o += 2 * RBH * AMAX;
     s.mu = o; o += RBH * AMAX;       // action-head outputs (means / logits)
-    s.bar = o; o += 4;               // two 8-byte mbarriers (one per chunk buffer)
+    s.bar = o; o += 8;               // four 8-byte mbarriers: one per chunk buffer (TMA), pair exchange, norm exchange
     s.scratch = o; o += 128;
     s.xch = o; o += 2 * 8 * 2;       // [parity][cluster rank][{sumsq, stop}]
     s.pay = o; o += NP * NTT;        // the partner CTA's gradient fragments land here (DSMEM stores)
@@ -295,6 +295,8 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
     const int LDX = a.DP, KP = a.KP, D = a.D;
     // payload of the pair exchange: gradient fragments + the five loss partial sums (thread 0)
     constexpr int NP = (NTW2 * 4 + NT1 * 4 + 4 + 1 + 5 + 3) / 4 * 4;
+    constexpr int PAY_V4 = NTW2 + NT1 + 3;      // float4 groups every thread sends to its partner per step
+    static_assert(PAY_V4 * 4 <= NP, "PAY too small");
     const PpoSmem L = ppo_smem_layout(LDX, NP);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int crank = (int)cluster_ctarank();       // cluster rank: trunk = crank / 2 (0 pi, 1 vf, 2 cvf), half = crank % 2
@@ -407,6 +409,8 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
     if (tid == 0) {
         mbar_init(&BAR[0], 1);
         mbar_init(&BAR[1], 1);
+        mbar_init(&BAR[2], 1);     // pair exchange: armed by thread 0 every step, completed by the partner's st.async bytes
+        mbar_init(&BAR[3], 1);     // norm exchange: completed by one 8-byte st.async from each CTA of the cluster
         fence_mbar_init();
     }
     __syncthreads();
@@ -491,9 +495,16 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                 const uint32_t local = smem_u32(PAY + 4 * tid);
                 asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(pay_remote) : "r"(local), "r"((uint32_t)(crank ^ 1)));
             }
+            // st.async: the store completes 16 transaction bytes on the PARTNER's pair-exchange mbarrier when it lands, so the
+            // receiver waits on its own mbarrier instead of a cluster barrier
+            uint32_t pbar_remote = 0;
+            if (working) {
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(pbar_remote) : "r"(smem_u32(&BAR[2])), "r"((uint32_t)(crank ^ 1)));
+            }
             auto st4 = [&](int v4, float x, float y, float z, float w) {
-                asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(pay_remote + (uint32_t)(v4 * NTT * 16)),
-                             "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                                 pay_remote + (uint32_t)(v4 * NTT * 16)),
+                             "f"(x), "f"(y), "f"(z), "f"(w), "r"(pbar_remote) : "memory");
             };
             if (working) {
                 for (int c0 = 0; c0 < Bn; c0 += RB, ++q) {
@@ -505,6 +516,13 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                     const float* Ac = ACT + buf * RBH * AMAX;   // rows at stride AP (as the stream stores them)
                     mbar_wait(&BAR[buf], (uint32_t)((q >> 1) & 1));
                     __syncthreads();          // chunk q landed, and everybody is done with chunk q-1's buffers
+                    if (c0 == 0 && tid == 0) {
+                        // arm this step's exchange barriers.  After the __syncthreads above no thread of this CTA is still
+                        // waiting on the previous phase, and bytes that arrive before the arming are accounted for (the
+                        // phase cannot complete without this arrival).
+                        mbar_expect_tx(&BAR[2], (uint32_t)(PAY_V4 * NTT * 16));
+                        mbar_expect_tx(&BAR[3], (uint32_t)(NCTA * 8));
+                    }
                     ICRL_MARK(0)
                     {
                         const Cursor nxt = cur_next(cur);
@@ -853,7 +871,8 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                 st4(NTW2 + NT1 + 1, g_s, t0 ? tot[0] : 0.f, t0 ? tot[1] : 0.f, t0 ? tot[2] : 0.f);
                 st4(NTW2 + NT1 + 2, t0 ? tot[3] : 0.f, t0 ? tot[4] : 0.f, 0.f, 0.f);
             }
-            cluster_sync_all();
+            // all of the partner's words of this step have landed (bounded: a vanished partner ends the launch with an error)
+            if (*(volatile float*)&XCH[31] == 0.f && !mbar_wait_bounded(&BAR[2], (uint32_t)(step & 1), 2000000000LL)) XCH[31] = 1.f;
             if (working) {
                 auto ld4 = [&](int v4) { return *reinterpret_cast<const float4*>(PAY + (v4 * NTT + tid) * 4); };
                 int v4 = 0;
@@ -1120,10 +1139,15 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                 if (a.max_steps > 0 && step + 1 >= a.max_steps) stop_flag = 2.f;
             }
             if (tid < ncta && working) {
-                st_remote_f32(XCH + (parity * 8 + crank) * 2 + 0, (uint32_t)tid, ss);
-                st_remote_f32(XCH + (parity * 8 + crank) * 2 + 1, (uint32_t)tid, stop_flag);
+                uint32_t ra, rb;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(XCH + (parity * 8 + crank) * 2)), "r"((uint32_t)tid));
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(smem_u32(&BAR[3])), "r"((uint32_t)tid));
+                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(ra),
+                             "f"(ss), "f"(stop_flag), "r"(rb) : "memory");
             }
-            cluster_sync_all();
+            // every CTA waits for the words of ALL six CTAs (it uses the even ranks' values): no CTA can run a step ahead of
+            // a peer that is still reading this step's exchange buffers
+            if (*(volatile float*)&XCH[31] == 0.f && !mbar_wait_bounded(&BAR[3], (uint32_t)(step & 1), 2000000000LL)) XCH[31] = 1.f;
             ICRL_MARK(9)
             const float total_ss = XCH[(parity * 8 + 0) * 2] + XCH[(parity * 8 + 2) * 2] + XCH[(parity * 8 + 4) * 2];
             const float stop_rx = XCH[(parity * 8 + 0) * 2 + 1];
