@@ -111,7 +111,7 @@ constexpr int NTW2 = 4;        // n-tiles of a 64 x 64 output per warp (warp til
 
 // ---------------------------------------------------------------- shared memory carve-up (float offsets)
 struct PpoSmem {
-    int w1, w2, b1, b2, hw, hb, logstd, sig, x, h1, h2, dh, rowf, dmean, act, mu, bar, scratch, xch, pay, total_bytes;
+    int w1, w2, b1, b2, hw, hb, logstd, sig, x, h1, h2, dh, rowf, dmean, act, mu, part, bar, scratch, xch, pay, total_bytes;
 };
 __host__ __device__ inline PpoSmem ppo_smem_layout(int LDX, int NP) {
     PpoSmem s;
@@ -132,6 +132,7 @@ __host__ __device__ inline PpoSmem ppo_smem_layout(int LDX, int NP) {
     s.dmean = o; o += RBH * AMAX;
     s.act = o; o += 2 * RBH * AMAX;
     s.mu = o; o += RBH * AMAX;       // action-head outputs (means / logits)
+    s.part = o; o += NWT * RBH * AMAX; // per-warp K-slice partials of the action head; later reused as the [16][LDH] dHW staging tile
     s.bar = o; o += 8;               // four 8-byte mbarriers: one per chunk buffer (TMA), pair exchange, norm exchange
     s.scratch = o; o += 128;
     s.xch = o; o += 2 * 8 * 2;       // [parity][cluster rank][{sumsq, stop}]
@@ -312,6 +313,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
     float* LOGSTD = sm + L.logstd; float* SIG = sm + L.sig;
     float* X = sm + L.x; float* H1 = sm + L.h1; float* H2 = sm + L.h2; float* DH = sm + L.dh;
     float* ROWF = sm + L.rowf; float* DMEAN = sm + L.dmean; float* ACT = sm + L.act; float* MU = sm + L.mu;
+    float* PART = sm + L.part;
     uint64_t* BAR = reinterpret_cast<uint64_t*>(sm + L.bar);
     float* scratch = sm + L.scratch;
     float* XCH = sm + L.xch;
@@ -368,6 +370,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
     if (tid < H) { B1[tid] = 0.f; B2[tid] = 0.f; }
     if (tid < AMAX) { HB[tid] = 0.f; LOGSTD[tid] = 0.f; }
     if (tid < 32) XCH[tid] = 0.f;
+    for (int i = tid; i < RBH * AMAX; i += NTT) DMEAN[i] = 0.f;   // unused head columns stay zero (they feed the MMA tiles)
     __syncthreads();
 #pragma unroll
     for (int nt = 0; nt < NTW2; ++nt)
@@ -559,8 +562,51 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                         warp_gemm_3xtf32<2, H>(acc, H1 + 16 * mtf * LDH, LDH, 1, W2, 1, LDH, H, 16 * ngf, 8, H, g, t);
 #pragma unroll
                         for (int nt = 0; nt < 2; ++nt) {
-                            *reinterpret_cast<float2*>(H2 + ojf * LDH + fw_k(nt)) = make_float2(tanhf(acc[nt][0]), tanhf(acc[nt][1]));
-                            *reinterpret_cast<float2*>(H2 + (ojf + 8) * LDH + fw_k(nt)) = make_float2(tanhf(acc[nt][2]), tanhf(acc[nt][3]));
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) acc[nt][c] = tanhf(acc[nt][c]);
+                            *reinterpret_cast<float2*>(H2 + ojf * LDH + fw_k(nt)) = make_float2(acc[nt][0], acc[nt][1]);
+                            *reinterpret_cast<float2*>(H2 + (ojf + 8) * LDH + fw_k(nt)) = make_float2(acc[nt][2], acc[nt][3]);
+                        }
+                        if (role == 0) {
+                            // action head, fused into this epilogue: the warp's 16 x 16 tile of H2 is still in registers in the
+                            // MMA C layout; with the K index permuted (k' = 2t -> slot t, 2t + 1 -> slot t + 4, the same
+                            // permutation applied to the HW operand) it IS an A fragment, so the warp multiplies its tile by
+                            // its 16-column slice of HW^T right away.  The four partial [16 x A] tiles of a row block meet
+                            // in PART after the barrier.
+                            const int nmaxA = (a.A + 7) & ~7;
+                            float pacc[2][4];
+#pragma unroll
+                            for (int no = 0; no < 2; ++no)
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) pacc[no][c] = 0.f;
+#pragma unroll
+                            for (int nt = 0; nt < 2; ++nt) {
+                                uint32_t ahi[4], alo[4];
+                                split_tf32(acc[nt][0], ahi[0], alo[0]);
+                                split_tf32(acc[nt][2], ahi[1], alo[1]);
+                                split_tf32(acc[nt][1], ahi[2], alo[2]);
+                                split_tf32(acc[nt][3], ahi[3], alo[3]);
+#pragma unroll
+                                for (int no = 0; no < 2; ++no) {
+                                    if (8 * no < nmaxA) {
+                                        const float2 b = *reinterpret_cast<const float2*>(HW + (8 * no + g) * WA_LD + fw_k(nt));
+                                        uint32_t bhi[2], blo[2];
+                                        split_tf32(b.x, bhi[0], blo[0]);
+                                        split_tf32(b.y, bhi[1], blo[1]);
+                                        mma_tf32(pacc[no], alo, bhi);
+                                        mma_tf32(pacc[no], ahi, blo);
+                                        mma_tf32(pacc[no], ahi, bhi);
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int no = 0; no < 2; ++no) {
+                                if (8 * no < nmaxA) {
+                                    float* pp = PART + (ngf * RBH + ojf) * AMAX + 8 * no + 2 * t;
+                                    *reinterpret_cast<float2*>(pp) = make_float2(pacc[no][0], pacc[no][1]);
+                                    *reinterpret_cast<float2*>(pp + 8 * AMAX) = make_float2(pacc[no][2], pacc[no][3]);
+                                }
+                            }
                         }
                     }
                     __syncthreads();
@@ -568,27 +614,21 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
 
                     // ---- heads + losses + d(loss)/d(head output).  8 threads per row (hr < RBH, hq < 8).
                     if (role == 0) {
-                        // action head: outputs d = hq, hq + 8
+                        // outputs d = hq, hq + 8 of row hr
                         float out[2];
 #pragma unroll
                         for (int u = 0; u < 2; ++u) {
                             const int d = hq + 8 * u;
                             float acc = 0.f;
                             if (d < a.A) {
-                                const float4* hrow = reinterpret_cast<const float4*>(H2 + hr * LDH);
-                                const float4* wrow = reinterpret_cast<const float4*>(HW + d * WA_LD);
-                                float p0 = HB[d], p1 = 0.f, p2 = 0.f, p3 = 0.f;     // 4 independent chains
+                                acc = HB[d];
 #pragma unroll
-                                for (int k = 0; k < H / 4; ++k) {
-                                    const float4 h = hrow[k], w = wrow[k];
-                                    p0 = fmaf(h.x, w.x, p0); p1 = fmaf(h.y, w.y, p1);
-                                    p2 = fmaf(h.z, w.z, p2); p3 = fmaf(h.w, w.w, p3);
-                                }
-                                acc = (p0 + p1) + (p2 + p3);
+                                for (int q4 = 0; q4 < 4; ++q4) acc += PART[(q4 * RBH + hr) * AMAX + d];   // the four column groups
                             }
                             out[u] = acc;
                             MU[hr * AMAX + d] = acc;
                         }
+                        ICRL_MARK(11)
                         const bool valid = hr < rows;
                         float logp = 0.f, ent = 0.f;
                         float dcoef[2] = {0.f, 0.f};   // d logp / d out[u]
@@ -713,21 +753,21 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                         }
                         if (hq == 0) { DMEAN[hr * AMAX + 0] = dV; }
                     }
+                    ICRL_MARK(12)
                     __syncthreads();
                     ICRL_MARK(4)
 
-                    // ---- head weight / bias / log_std gradients (rows beyond `rows` carry zero dmean: loops run over RB)
-                    if (hd < AOUT) {
-                        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-#pragma unroll 8
-                        for (int r = 0; r < RBH; ++r) {
-                            const float dm = DMEAN[r * AMAX + hd];
-                            const float4 h = *reinterpret_cast<const float4*>(H2 + r * LDH + 4 * hk4);
-                            acc0 = fmaf(dm, h.x, acc0); acc1 = fmaf(dm, h.y, acc1);
-                            acc2 = fmaf(dm, h.z, acc2); acc3 = fmaf(dm, h.w, acc3);
-                        }
-                        g_hw[0] += acc0; g_hw[1] += acc1; g_hw[2] += acc2; g_hw[3] += acc3;
+                    // ---- head weight gradient G[d][k] = sum_r dmean[r][d] H2[r][k] on tensor cores (rows beyond `rows` carry zero
+                    // dmean): warp w owns columns [8w, 8w + 8); the tile is staged in shared memory and added by the owner
+                    // threads after the next barrier
+                    {
+                        float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+                        warp_gemm_3xtf32<1, RBH>(acc, DMEAN, 1, AMAX, H2 + 8 * warp, LDH, 1, RBH, 0, 8, 8, g, t);
+                        float* sp = PART + g * LDH + 8 * warp + 2 * t;
+                        *reinterpret_cast<float2*>(sp) = make_float2(acc[0][0], acc[0][1]);
+                        *reinterpret_cast<float2*>(sp + 8 * LDH) = make_float2(acc[0][2], acc[0][3]);
                     }
+                    ICRL_MARK(13)
                     if (s_kind == 2) {
                         float acc = 0.f;
 #pragma unroll 8
@@ -744,34 +784,35 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                         }
                         g_s += acc - a.ent_coef * (float)rows * invB;
                     }
-                    // ---- dH2pre[r][k] = (sum_d dmean[r][d] * HW[d][k]) * (1 - H2^2)   (thread: row hr, k in [8hq, 8hq+8))
+                    ICRL_MARK(14)
+                    // ---- dH2pre[r][k] = (sum_d dmean[r][d] * HW[d][k]) * (1 - H2^2) on tensor cores   (K = padded head width)
                     {
-                        float dloc[8];
+                        float acc[2][4];
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) dloc[k] = 0.f;
-                        for (int d = 0; d < AOUT; ++d) {
-                            const float dm = DMEAN[hr * AMAX + d];
-                            const float4* wrow = reinterpret_cast<const float4*>(HW + d * WA_LD + 8 * hq);
+                        for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-                            for (int k = 0; k < 2; ++k) {
-                                const float4 w = wrow[k];
-                                dloc[4 * k + 0] = fmaf(dm, w.x, dloc[4 * k + 0]);
-                                dloc[4 * k + 1] = fmaf(dm, w.y, dloc[4 * k + 1]);
-                                dloc[4 * k + 2] = fmaf(dm, w.z, dloc[4 * k + 2]);
-                                dloc[4 * k + 3] = fmaf(dm, w.w, dloc[4 * k + 3]);
-                            }
-                        }
-                        const float4* hrow = reinterpret_cast<const float4*>(H2 + hr * LDH + 8 * hq);
-                        float4* drow = reinterpret_cast<float4*>(DH + hr * LDH + 8 * hq);
+                            for (int c = 0; c < 4; ++c) acc[nt][c] = 0.f;
+                        if (AOUT > 8)
+                            warp_gemm_3xtf32<2, 16>(acc, DMEAN + 16 * mtf * AMAX, AMAX, 1, HW, WA_LD, 1, 16, 16 * ngf, 8, H, g, t);
+                        else
+                            warp_gemm_3xtf32<2, 8>(acc, DMEAN + 16 * mtf * AMAX, AMAX, 1, HW, WA_LD, 1, 8, 16 * ngf, 8, H, g, t);
 #pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            const float4 h = hrow[k];
-                            drow[k] = make_float4(dloc[4 * k + 0] * (1.f - h.x * h.x), dloc[4 * k + 1] * (1.f - h.y * h.y),
-                                                  dloc[4 * k + 2] * (1.f - h.z * h.z), dloc[4 * k + 3] * (1.f - h.w * h.w));
+                        for (int nt = 0; nt < 2; ++nt) {
+                            const float2 ha = *reinterpret_cast<const float2*>(H2 + ojf * LDH + fw_k(nt));
+                            const float2 hb = *reinterpret_cast<const float2*>(H2 + (ojf + 8) * LDH + fw_k(nt));
+                            *reinterpret_cast<float2*>(DH + ojf * LDH + fw_k(nt)) =
+                                make_float2(acc[nt][0] * (1.f - ha.x * ha.x), acc[nt][1] * (1.f - ha.y * ha.y));
+                            *reinterpret_cast<float2*>(DH + (ojf + 8) * LDH + fw_k(nt)) =
+                                make_float2(acc[nt][2] * (1.f - hb.x * hb.x), acc[nt][3] * (1.f - hb.y * hb.y));
                         }
                     }
+                    ICRL_MARK(15)
                     __syncthreads();
                     ICRL_MARK(5)
+                    if (hd < AOUT) {
+                        const float4 v = *reinterpret_cast<const float4*>(PART + hd * LDH + 4 * hk4);
+                        g_hw[0] += v.x; g_hw[1] += v.y; g_hw[2] += v.z; g_hw[3] += v.w;
+                    }
 
                     // ---- dW2[j][k] += sum_r dH2pre[r][j] H1[r][k]   (A = dH2pre^T read in place, B = H1)
                     warp_gemm_3xtf32<NTW2, RBH>(g_w2, DH + 16 * mt, 1, LDH, H1, LDH, 1, RBH, 32 * ng, 8, H, g, t);
@@ -1384,7 +1425,8 @@ static int ppo_train_impl(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, fl
             fprintf(stderr, "[ppo timing] cta %d cycles/step:", r);
             double tot = 0;
             for (int i = 0; i < 11; ++i) { fprintf(stderr, " %s=%.0f", names[i], h[r * 16 + i] / steps); tot += h[r * 16 + i] / steps; }
-            fprintf(stderr, " total=%.0f\n", tot);
+            fprintf(stderr, " total=%.0f | of which head: dot=%.0f logp=%.0f, headgrad: dHW=%.0f bias/logstd=%.0f dH2=%.0f\n", tot + (h[r*16+11]+h[r*16+12]+h[r*16+13]+h[r*16+14]+h[r*16+15]) / steps,
+                    h[r * 16 + 11] / steps, h[r * 16 + 12] / steps, h[r * 16 + 13] / steps, h[r * 16 + 14] / steps, h[r * 16 + 15] / steps);
         }
     }
     return rc;
