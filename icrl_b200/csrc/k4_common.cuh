@@ -20,10 +20,10 @@ constexpr float HALF_LOG_2PI_PLUS_HALF = 1.4189385332046727418f;
 // K extent of the obs GEMMs (multiple of the mma K = 8) and the row stride of obs tiles / W1 / the obs stream
 __host__ __device__ inline int ppo_kp(int D) { return (D + 7) / 8 * 8; }
 __host__ __device__ inline int ppo_ldx(int D) {
-    const int kp = ppo_kp(D);
+    const int kp = (D + 15) / 16 * 16;   // the dW1 n-tiles come in pairs (one per warp group): rows are padded to 16 columns
     int ld = kp / 32 * 32 + 4;
     if (ld < kp) ld += 32;
-    return ld;                 // >= kp, == 4 (mod 32), multiple of 4 floats (16-byte rows for the TMA bulk copies)
+    return ld;                 // >= round16(D), == 4 (mod 32), multiple of 4 floats (16-byte rows for the TMA bulk copies)
 }
 
 struct PpoArgs {

@@ -70,7 +70,9 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 // Fragment layout (PTX ISA, m16n8k8 .tf32): g = lane >> 2, t = lane & 3;
 //   a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);  b0 (k = t, n = g) b1 (k = t+4, n = g);
 //   c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
-template <int NT, int KC = 0>
+// GUARD: skip n-tiles at or beyond nmax (a per-tile branch: it keeps ptxas from interleaving the independent MMA chains of
+// different n-tiles, so it is only instantiated where a tile can really fall outside the operand)
+template <int NT, int KC = 0, bool GUARD = false>
 __device__ __forceinline__ void warp_gemm_3xtf32(float (&c)[NT][4], const float* __restrict__ A, int sam, int sak,
                                                  const float* __restrict__ B, int sbk, int sbn, int K, int ncol0, int nstep,
                                                  int nmax, int g, int t) {
@@ -88,7 +90,7 @@ __device__ __forceinline__ void warp_gemm_3xtf32(float (&c)[NT][4], const float*
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
             const int n0 = ncol0 + i * nstep;
-            if (n0 < nmax) {
+            if (!GUARD || n0 < nmax) {
                 uint32_t bhi[2], blo[2];
                 const float* bp = B + (k0 + t) * sbk + (n0 + g) * sbn;
                 split_tf32(bp[0], bhi[0], blo[0]);
@@ -542,7 +544,14 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                             const float2 b = *reinterpret_cast<const float2*>(B1 + fw_k(nt));
                             acc[nt][0] = b.x; acc[nt][1] = b.y; acc[nt][2] = b.x; acc[nt][3] = b.y;
                         }
-                        warp_gemm_3xtf32<2>(acc, Xc + 16 * mtf * LDX, LDX, 1, W1, 1, LDX, KP, 16 * ngf, 8, H, g, t);
+                        // compile-time trip count for the two K values that map to this NT1 exactly (all named workloads): fully
+                        // unrolled, so the fragment loads of later k-steps are issued ahead of the MMAs
+                        if (KP == 16 * NT1)
+                            warp_gemm_3xtf32<2, 16 * NT1>(acc, Xc + 16 * mtf * LDX, LDX, 1, W1, 1, LDX, 16 * NT1, 16 * ngf, 8, H, g, t);
+                        else if (KP == 16 * NT1 - 8)
+                            warp_gemm_3xtf32<2, 16 * NT1 - 8>(acc, Xc + 16 * mtf * LDX, LDX, 1, W1, 1, LDX, 16 * NT1 - 8, 16 * ngf, 8, H, g, t);
+                        else
+                            warp_gemm_3xtf32<2>(acc, Xc + 16 * mtf * LDX, LDX, 1, W1, 1, LDX, KP, 16 * ngf, 8, H, g, t);
 #pragma unroll
                         for (int nt = 0; nt < 2; ++nt) {
                             *reinterpret_cast<float2*>(H1 + ojf * LDH + fw_k(nt)) = make_float2(tanhf(acc[nt][0]), tanhf(acc[nt][1]));
@@ -848,7 +857,12 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                     __syncthreads();
                     ICRL_MARK(6)
                     // ---- dW1[j][k] += sum_r dH1pre[r][j] X[r][k] ; db1
-                    warp_gemm_3xtf32<NT1, RBH>(g_w1, H2 + 16 * mt, 1, LDH, Xc, LDX, 1, RBH, 8 * ng, 16, KP, g, t);
+                    // every warp group has NT1 n-tiles inside the (zero padded) row when round16(D) == 16 NT1 -- true for all the
+                    // named workloads; otherwise the last tile of the second group is skipped by the guarded variant
+                    if (((KP + 15) & ~15) == 16 * NT1)
+                        warp_gemm_3xtf32<NT1, RBH, false>(g_w1, H2 + 16 * mt, 1, LDH, Xc, LDX, 1, RBH, 8 * ng, 16, KP, g, t);
+                    else
+                        warp_gemm_3xtf32<NT1, RBH, true>(g_w1, H2 + 16 * mt, 1, LDH, Xc, LDX, 1, RBH, 8 * ng, 16, KP, g, t);
                     if (s_kind == 0) {
                         float acc = 0.f;
 #pragma unroll 8
