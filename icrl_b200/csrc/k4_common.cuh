@@ -49,12 +49,14 @@ struct PpoArgs {
     float* recv[ICRL_PPO_MAX_RANKS];
     unsigned int* flags[ICRL_PPO_MAX_RANKS];
     unsigned int flag_base;
-    int dist_mode;                // 0 auto (reduce-scatter/all-gather for 4 and 8 ranks, direct otherwise), 1 direct, 2 RS/AG
+    int dist_mode;                // 0 auto (tagged broadcast + sum for 2 / 4 ranks, RS/AG for 8, {value, seq} words otherwise),
+                                  // 1 {value, seq} words, 2 RS/AG, 3 broadcast + sum   (ICRL_PPO_DIST_MODE)
     const double* advsums;        // all-reduced per-step sums (sum adv_r, sum adv_r^2, sum adv_c, count) or NULL
 };
 constexpr int DIST_SLOTS = 72;    // floats per thread in a receive-buffer slab
-constexpr int RSAG_MAXW = 10;     // 16-byte words per (rank, role, thread) slab of the reduce-scatter / all-gather exchange:
-                                  // layout [region 2][parity 2][src 8][role 3][RSAG_MAXW][256 threads] uint4 = 3.9 MB,
+constexpr int RSAG_MAXW = 20;     // 16-byte words per (rank, role, thread) slab of the reduce-scatter / all-gather exchange:
+                                  // layout [region 3][parity 2][src 8][role 3][RSAG_MAXW][256 threads] uint4 = 11.8 MB (regions: reduce-scatter, all-gather,
+                                  // 2-rank broadcast),
                                   // overlaid on the same receive buffer (sequence numbers keep the two layouts apart)
 
 inline int ppo_fill_offsets(PpoArgs& a) {
