@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--workload", default="halfcheetah")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-steps", type=int, default=300, help="K4 optimiser steps in the CPU sample")
+    ap.add_argument("--cpu-steps", type=int, default=1600, help="K4 optimiser steps in the CPU sample (one full HalfCheetah rollout)")
     ap.add_argument("--replicas", action="store_true", help="N>1: independent learners instead of data-parallel all-reduce")
     return ap.parse_args()
 
@@ -190,12 +190,29 @@ def cpu_iteration_estimate(w, k4_steps, seed=0):
     return est, t, sample
 
 
+def pick_cpu_threads(w):
+    """The oracle's tensors are tiny (64-128 rows x 64 units): torch's intra-op threading can cost more than it gives.
+    Time a few K4 optimiser steps with every host core and with one thread, keep the faster setting -- the CPU arm gets
+    whatever thread count serves it best on this box."""
+    cores = os.cpu_count() or 1
+    best, best_t = cores, None
+    for n in sorted({cores, max(1, cores // 4), 1}, reverse=True):
+        th.set_num_threads(n)
+        cpu_iteration_estimate(w, 8)                       # warm the thread pool / autograd
+        t0 = time.perf_counter()
+        _, parts, _ = cpu_iteration_estimate(w, 24)
+        t = parts["k4"]
+        if best_t is None or t < best_t:
+            best, best_t = n, t
+    th.set_num_threads(best)
+    return best
+
+
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    th.set_num_threads(cores)
+    cores = pick_cpu_threads(w)
     for _ in range(max(args.warmup, 1) - 1):
         cpu_iteration_estimate(w, max(20, args.cpu_steps // 10))
     ests, parts, sample = [], None, ""
@@ -453,8 +470,7 @@ def main():
         roof = kernel_roofline(learner, peak, peak_src)
         fam = family_rooflines(learner, peak)
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
-        th.set_num_threads(cores)
+        cores = pick_cpu_threads(w)
         est, parts, sample = cpu_iteration_estimate(w, args.cpu_steps)
         cpu = {"value": w.transitions_per_iteration / est, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                "seconds_per_iteration_est": round(est, 2), "seconds_per_part": {k: round(v, 4) for k, v in parts.items()}}
