@@ -51,7 +51,7 @@ __host__ __device__ inline CnSmem cn_smem_layout(const CnPlan& p, int HP, int TI
     off = align_up(off, 16);
     for (int l = 0; l < ICRL_MAX_HIDDEN; ++l) {
         s.w[l] = off;
-        if (l < p.n_hidden) off += (l == 0 ? p.n_select : HP) * HP * 4;
+        if (l < p.n_hidden) off += (l == 0 ? align_up(p.n_select, 8) : HP) * HP * 4;   // zero rows pad layer 0 to whole k-steps
         s.b[l] = off;
         if (l < p.n_hidden) off += HP * 4;
     }
@@ -71,7 +71,7 @@ __device__ __forceinline__ void cn_load_weights(const CnPlan& p, const CnSmem& L
     int in_dim = p.n_select;
     for (int l = 0; l < p.n_hidden; ++l) {
         const int out_dim = p.hidden[l];
-        const int kpad = (l == 0) ? p.n_select : HP;
+        const int kpad = (l == 0) ? align_up(p.n_select, 8) : HP;
         float* W = reinterpret_cast<float*>(smem + L.w[l]);
         float* B = reinterpret_cast<float*>(smem + L.b[l]);
         for (int i = threadIdx.x; i < kpad * HP; i += blockDim.x) {

@@ -124,6 +124,21 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
+// ---- tensor-core helpers (mma.sync m16n8k8, TF32 operands, fp32 accumulate) shared by K1 and K4
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    // hi = x with the 13 low mantissa bits cleared (one LOP3; cvt.rna.tf32 expands to a multi-instruction sequence and
+    // was 29% of all issued instructions), lo = x - hi exactly.  x = hi + lo holds exactly, hi is a valid TF32 value and
+    // the tensor core keeps 11 significant bits of lo (<= 2^-10 |x|): ~2^-20 relative per product, fp32-class.
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
 // streaming (read-once) global loads that do not pollute L1
 __device__ __forceinline__ float ld_stream(const float* p) {
     float v;

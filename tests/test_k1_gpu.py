@@ -127,3 +127,17 @@ def test_unaligned_base_pointer_falls_back():
     th.cuda.synchronize()
     want = ocn.cost_function(cn_params(d), cn_spec("hc", d), obs.cpu().numpy(), acs.cpu().numpy())
     assert_cost_close(out.cpu().numpy(), want)
+
+
+def test_tensor_core_variant_matches_goldens():
+    """The opt-in mma.sync variant of K1 (ICRL_K1_MMA=1; read once per process) against the same golden fixtures."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, ICRL_K1_MMA="1", ICRL_K1_MMA_CHILD="1")
+    if os.environ.get("ICRL_K1_MMA_CHILD"):
+        pytest.skip("already inside the child run")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-x", "-k", "golden or checkpoint or ragged or 3d"],
+                       env=env, capture_output=True, text=True, timeout=600, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
