@@ -34,7 +34,17 @@ def cpg(config):
     elif config.cn_path is None:
         cost_function = get_true_cost_function(config.eval_env_id)
     elif config.load_gail:
-        raise NotImplementedError("GAIL discriminators (icrl/gail_utils.py) are outside the ICRL hot path")
+        from icrl_b200.gail_utils import GailDiscriminator
+        action_low = action_high = None
+        if not is_discrete:
+            action_low, action_high = train_env.action_space.low, train_env.action_space.high
+        gail = GailDiscriminator.load(config.cn_path, obs_dim=obs_dim, acs_dim=acs_dim, is_discrete=is_discrete,
+                                      obs_select_dim=config.cn_obs_select_dim, acs_select_dim=config.cn_acs_select_dim,
+                                      clip_obs=None, obs_mean=None, obs_var=None, action_low=action_low,
+                                      action_high=action_high, device=config.cn_device or "auto")
+
+        def cost_function(obs, acs):
+            return gail.reward_function(obs, acs, apply_log=False)
     else:
         action_low = action_high = None
         if not is_discrete:

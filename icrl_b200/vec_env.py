@@ -152,6 +152,8 @@ class VecCostWrapper(VecEnvWrapper):
         obs, rews, news, infos = self.venv.step_wait()
         if self.cost_function is not None:
             cost = self.cost_function(self.previous_obs.copy(), self.actions.copy())
+            cost = np.atleast_1d(cost)    # GailDiscriminator.reward_function squeezes a single-env batch to 0-d (the reference
+                                          # would raise on cost[i] there)
             for i in range(len(infos)):
                 infos[i][self.cost_info_str] = cost[i]
         self.previous_obs = obs.copy()

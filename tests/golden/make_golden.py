@@ -388,6 +388,26 @@ def golden_ckpt():
              adam_step=np.int64(osd["state"][osd["param_groups"][0]["params"][0]]["step"]))
 
 
+# ------------------------------------------------------------------------------------------- GAIL discriminator as a cost
+def golden_gail():
+    """The reference's GailDiscriminator.load + reward_function on its two shipped `gail_discriminator.pt` files (copied
+    as DATA fixtures), for seeded inputs."""
+    import shutil
+    from icrl.gail_utils import GailDiscriminator
+    rng = np.random.default_rng(23)
+    for name in ("AntBroken", "Point"):
+        src = os.path.join(REF, "icrl/expert_data/ConstraintTransfer/GAIL", name, "files/gail_discriminator.pt")
+        dst = os.path.join(OUT, f"ref_gail_{name.lower()}.pt")
+        shutil.copyfile(src, dst)
+        os.chmod(dst, 0o644)
+        gail = GailDiscriminator.load(src, device="cpu")
+        obs = (rng.standard_normal((257, gail.obs_dim)) * 3).astype(np.float32)
+        acs = rng.uniform(-1.5, 1.5, (257, gail.acs_dim)).astype(np.float32)
+        obs3, acs3 = obs[:60].reshape(12, 5, -1), acs[:60].reshape(12, 5, -1)
+        save(f"gail_{name.lower()}", obs=obs, acs=acs, d=gail.reward_function(obs, acs, apply_log=False),
+             logd=gail.reward_function(obs, acs, apply_log=True), d3=gail.reward_function(obs3, acs3, apply_log=False))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["k1", "k2", "k3", "k4"]
     for w in which:

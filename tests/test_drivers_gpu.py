@@ -72,3 +72,27 @@ def test_run_me_cpg_run_policy_icrl(tmp_path):
     assert os.path.exists(os.path.join(icrl_dir, "best_cn_model.pt"))
     assert os.path.exists(os.path.join(icrl_dir, "models", "icrl_1_itrs", "nominal_agent.zip"))
     assert "Beginning training" in out
+
+
+def test_run_me_cpg_with_frozen_constraint_net_and_gail(tmp_path):
+    """`cpg --cn_path <cn.pt>` (K1 per env step through VecCostWrapper) and `cpg --load_gail --cn_path <gail.pt>`."""
+    import torch as th
+    from icrl_b200.constraint_net import ConstraintNet
+    env = dict(os.environ, ICRL_SAVE_ROOT=str(tmp_path / "runs"))
+    rng = np.random.default_rng(0)
+    cn = ConstraintNet(18, 6, (20,), None, lambda _: 1e-3, rng.standard_normal((20, 18)), rng.standard_normal((20, 6)), False,
+                       0.5, clip_obs=20)
+    cn_path = str(tmp_path / "cn.pt")
+    cn.save(cn_path)
+    common = ["-tei", "SynthHCWithPos-v0", "-eei", "SynthHCWithPosTest-v0", "-ns", "128", "-nt", "2", "-s", "2", "-t", "512",
+              "-ee", "128", "-se", "256"]
+    _run(["cpg"] + common + ["--cn_path", cn_path], env)
+    # a discriminator in the reference's gail_discriminator.pt schema with this env's shape
+    sd = th.load(os.path.join(GOLD, "ref_gail_point.pt"), weights_only=False)
+    net = {k: v.clone() for k, v in sd["network"].items()}
+    sd.update(obs_dim=18, acs_dim=6, obs_select_dim=[0, 1], acs_select_dim=[-1], action_low=-np.ones(6, np.float32),
+              action_high=np.ones(6, np.float32), network=net)
+    gail_path = str(tmp_path / "gail_discriminator.pt")
+    th.save(sd, gail_path)
+    _run(["cpg"] + common + ["--load_gail", "--cn_path", gail_path, "-cosd", "0", "1", "-casd", "-1"], env)
+    assert len(glob.glob(str(tmp_path / "runs" / "*" / "files" / "best_model.zip"))) == 2

@@ -141,3 +141,20 @@ def test_tensor_core_variant_matches_goldens():
                        env=env, capture_output=True, text=True, timeout=600, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout
+
+
+@pytest.mark.parametrize("name", ["antbroken", "point"])
+def test_gail_discriminator_reward_function(name):
+    """`cpg --load_gail`: the reference's shipped discriminators loaded by GailDiscriminator.load, evaluated by K1
+    (prediction output), against what the reference's own class returns (tests/golden/make_golden.py::golden_gail)."""
+    import os
+    from icrl_b200.gail_utils import GailDiscriminator
+    g = load_golden(f"gail_{name}")
+    gail = GailDiscriminator.load(os.path.join(os.path.dirname(__file__), "golden", f"ref_gail_{name}.pt"))
+    d = gail.reward_function(g["obs"], g["acs"], apply_log=False)
+    assert d.shape == g["d"].shape
+    np.testing.assert_allclose(d, g["d"], rtol=COST_RTOL, atol=COST_ATOL)
+    np.testing.assert_allclose(gail.reward_function(g["obs"], g["acs"], apply_log=True), g["logd"], rtol=1e-4, atol=1e-5)
+    d3 = gail.reward_function(g["obs"][:60].reshape(12, 5, -1), g["acs"][:60].reshape(12, 5, -1), apply_log=False)
+    assert d3.shape == g["d3"].shape
+    np.testing.assert_allclose(d3, g["d3"], rtol=COST_RTOL, atol=COST_ATOL)

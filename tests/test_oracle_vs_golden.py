@@ -181,3 +181,20 @@ def test_costnorm_oracle_matches_reference_wrappers(name, norm):
     np.testing.assert_array_equal(out, g["cost"].astype(np.float32))
     assert state["mean"] == g["cost_rms_mean"] and state["var"] == g["cost_rms_var"]
     assert state["count"] == float(g["cost_rms_count"])
+
+
+# ------------------------------------------------------------------------------------------- GAIL discriminator cost (f4)
+@pytest.mark.parametrize("name", ["antbroken", "point"])
+def test_gail_discriminator_oracle_matches_reference(name):
+    """GailDiscriminator.reward_function = select dims -> MLP -> sigmoid with nothing else applied to nominal data
+    (gail_utils.py:233-250): the K1 oracle with clipping / normalisation switched off reproduces it bit for bit."""
+    import os
+    g = load_golden(f"gail_{name}")
+    sd = th.load(os.path.join(os.path.dirname(__file__), "golden", f"ref_gail_{name}.pt"), weights_only=False)
+    params = [sd["network"][k] for k in sd["network"]]
+    sel = ocn.define_select_dim(sd["obs_dim"], sd["acs_dim"], sd["obs_select_dim"], sd["acs_select_dim"])
+    spec = ocn.CNSpec(sd["obs_dim"], sd["acs_dim"], tuple(sd["hidden_sizes"]), False, obs_select_dim=sd["obs_select_dim"],
+                      acs_select_dim=sd["acs_select_dim"], clip_obs=None)
+    assert len(sel) == params[0].shape[1]
+    pred = 1.0 - ocn.cost_function(params, spec, g["obs"], g["acs"])
+    np.testing.assert_allclose(pred, g["d"], rtol=0, atol=6e-8)
