@@ -368,7 +368,9 @@ def kernel_roofline(learner, peak, peak_src):
             "launch_ms": dur * 1e3, "optimiser_steps_per_launch": steps, "us_per_optimiser_step": dur / steps * 1e6,
             "algorithmic_bytes_per_launch": alg_bytes,
             "note": "1600 dependent optimiser steps on 64-128 rows each: latency-bound by construction (SURVEY §7), "
-                    "so the HBM fraction is tiny; us_per_optimiser_step is the figure of merit"}
+                    "so the HBM fraction is tiny; us_per_optimiser_step is the figure of merit.  ncu on the same launch "
+                    "(profiles/SUMMARY_r01.md): tensor pipe active 20.6 %, 8 of 64 warp slots, the GEMM phases run at ~2x their "
+                    "mma.sync issue bound"}
 
 
 def family_rooflines(learner, peak):
