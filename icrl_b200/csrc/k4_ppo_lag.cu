@@ -894,9 +894,9 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                 }
                 return q2;
             };
-            // loss partial sums: warp-reduce only; lane 0 of every warp carries its warp's partial through the exchanges
-            // (slot-wise sums), the single block reduction after the exchanges totals them together with the gradient norm
-            float red[6] = {warp_sum(s_a), warp_sum(s_b), warp_sum(s_c), warp_sum(s_d), warp_sum(s_e), 0.f};
+            // loss partial sums: every thread carries its own partials through the exchanges (slot-wise sums); the single block
+            // reduction after the exchanges totals them together with the gradient norm
+            float red[6];
 
             // ---- (2) CTA-pair exchange through distributed shared memory: every thread stores its gradient fragments (and
             // thread 0 the loss sums) into the partner's PAY buffer as float4 groups straight from registers, cluster
@@ -904,7 +904,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
             // keep their weight copies identical.   Groups: g_w2[0..NTW2), g_w1[0..NT1), g_hw, {g_s, s0, s1, s2}, {s3, s4, -, -}
             float tot[5];                                                 // loss sums: this warp -> pair -> all ranks
 #pragma unroll
-            for (int i = 0; i < 5; ++i) tot[i] = (lane == 0) ? red[i] : 0.f;
+            for (int i = 0; i < 5; ++i) tot[i] = (i == 0) ? s_a : (i == 1) ? s_b : (i == 2) ? s_c : (i == 3) ? s_d : s_e;
             if (working) {
                 const bool t0 = true;   // every thread sends its slot (non-zero for lane 0 of each warp)
 #pragma unroll
