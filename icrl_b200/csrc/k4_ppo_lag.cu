@@ -58,7 +58,10 @@ __device__ __forceinline__ void st_remote_f32(float* local_ptr, uint32_t rank, f
 //   c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
 // GUARD: skip n-tiles at or beyond nmax (a per-tile branch: it keeps ptxas from interleaving the independent MMA chains of
 // different n-tiles, so it is only instantiated where a tile can really fall outside the operand)
-template <int NT, int KC = 0, bool GUARD = false>
+// KPERM: the summation index of a k-step is permuted (slot t <-> k0 + 2t, slot t + 4 <-> k0 + 2t + 1, on BOTH operands, which
+// leaves the product unchanged).  For operands whose K runs along shared-memory ROWS of stride == 4 (mod 32) this turns the
+// 2-way bank conflicts of the natural order (bank 4t + g) into conflict-free loads (banks 8t + g and 8t + 4 + g).
+template <int NT, int KC = 0, bool GUARD = false, bool KPERM = false>
 __device__ __forceinline__ void warp_gemm_3xtf32(float (&c)[NT][4], const float* __restrict__ A, int sam, int sak,
                                                  const float* __restrict__ B, int sbk, int sbn, int K, int ncol0, int nstep,
                                                  int nmax, int g, int t) {
@@ -67,20 +70,21 @@ __device__ __forceinline__ void warp_gemm_3xtf32(float (&c)[NT][4], const float*
     for (int k0 = 0; k0 < kend; k0 += 8) {
         uint32_t ahi[4], alo[4];
         {
-            const float* ap = A + (k0 + t) * sak + g * sam;
+            const float* ap = A + (k0 + (KPERM ? 2 * t : t)) * sak + g * sam;
+            const int ks = KPERM ? sak : 4 * sak;          // distance between the thread's two K slots
             split_tf32(ap[0], ahi[0], alo[0]);
             split_tf32(ap[8 * sam], ahi[1], alo[1]);
-            split_tf32(ap[4 * sak], ahi[2], alo[2]);
-            split_tf32(ap[4 * sak + 8 * sam], ahi[3], alo[3]);
+            split_tf32(ap[ks], ahi[2], alo[2]);
+            split_tf32(ap[ks + 8 * sam], ahi[3], alo[3]);
         }
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
             const int n0 = ncol0 + i * nstep;
             if (!GUARD || n0 < nmax) {
                 uint32_t bhi[2], blo[2];
-                const float* bp = B + (k0 + t) * sbk + (n0 + g) * sbn;
+                const float* bp = B + (k0 + (KPERM ? 2 * t : t)) * sbk + (n0 + g) * sbn;
                 split_tf32(bp[0], bhi[0], blo[0]);
-                split_tf32(bp[4 * sbk], bhi[1], blo[1]);
+                split_tf32(bp[KPERM ? sbk : 4 * sbk], bhi[1], blo[1]);
                 mma_tf32(c[i], alo, bhi);
                 mma_tf32(c[i], ahi, blo);
                 mma_tf32(c[i], ahi, bhi);
@@ -757,7 +761,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                     // threads after the next barrier
                     {
                         float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
-                        warp_gemm_3xtf32<1, RBH>(acc, DMEAN, 1, AMAX, H2 + 8 * warp, LDH, 1, RBH, 0, 8, 8, g, t);
+                        warp_gemm_3xtf32<1, RBH>(acc, DMEAN, 1, AMAX, H2 + 8 * warp, LDH, 1, RBH, 0, 8, 8, g, t);   // (DMEAN's stride 16 would turn KPERM into 4-way conflicts)
                         float* sp = PART + g * LDH + 8 * warp + 2 * t;
                         *reinterpret_cast<float2*>(sp) = make_float2(acc[0][0], acc[0][1]);
                         *reinterpret_cast<float2*>(sp + 8 * LDH) = make_float2(acc[0][2], acc[0][3]);
@@ -810,7 +814,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                     }
 
                     // ---- dW2[j][k] += sum_r dH2pre[r][j] H1[r][k]   (A = dH2pre^T read in place, B = H1)
-                    warp_gemm_3xtf32<NTW2, RBH>(g_w2, DH + 16 * mt, 1, LDH, H1, LDH, 1, RBH, 32 * ng, 8, H, g, t);
+                    warp_gemm_3xtf32<NTW2, RBH, false, true>(g_w2, DH + 16 * mt, 1, LDH, H1, LDH, 1, RBH, 32 * ng, 8, H, g, t);
                     if (last_chunk) {
 #pragma unroll
                         for (int i = 0; i < NTW2; ++i) st4(i, g_w2[i][0], g_w2[i][1], g_w2[i][2], g_w2[i][3]);
@@ -846,9 +850,9 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                     // every warp group has NT1 n-tiles inside the (zero padded) row when round16(D) == 16 NT1 -- true for all the
                     // named workloads; otherwise the last tile of the second group is skipped by the guarded variant
                     if (((KP + 15) & ~15) == 16 * NT1)
-                        warp_gemm_3xtf32<NT1, RBH, false>(g_w1, H2 + 16 * mt, 1, LDH, Xc, LDX, 1, RBH, 8 * ng, 16, KP, g, t);
+                        warp_gemm_3xtf32<NT1, RBH, false, true>(g_w1, H2 + 16 * mt, 1, LDH, Xc, LDX, 1, RBH, 8 * ng, 16, KP, g, t);
                     else
-                        warp_gemm_3xtf32<NT1, RBH, true>(g_w1, H2 + 16 * mt, 1, LDH, Xc, LDX, 1, RBH, 8 * ng, 16, KP, g, t);
+                        warp_gemm_3xtf32<NT1, RBH, true, true>(g_w1, H2 + 16 * mt, 1, LDH, Xc, LDX, 1, RBH, 8 * ng, 16, KP, g, t);
                     if (s_kind == 0) {
                         float acc = 0.f;
 #pragma unroll 8
