@@ -9,10 +9,14 @@
 //   * the minibatch schedule is data-independent, so two massively parallel prologue kernels take everything that does
 //     not depend on the parameters out of the step chain: the random-access gather (minibatch-ordered streams in HBM),
 //     the per-minibatch advantage statistics and the Adam bias corrections;
-//   * the three trunks (pi / vf / cvf) are independent networks (torch_layers.py:129-254), so each gets its own CTA of a
-//     3-CTA cluster -- model parallel with NO activation exchange.  The only coupling is clip_grad_norm_'s global norm:
-//     one float per CTA per step, exchanged through distributed shared memory + a cluster barrier;
-//   * each 64-row chunk arrives by TMA bulk copies (cp.async.bulk + mbarrier) issued one chunk ahead by a single thread;
+//   * the three trunks (pi / vf / cvf) are independent networks (torch_layers.py:129-254), so each gets its own CTA PAIR of
+//     a 6-CTA cluster (each CTA takes 32 rows of every 64-row chunk) -- model parallel with NO activation exchange.  A pair
+//     exchanges its gradient halves through distributed shared memory: st.async stores that complete transaction bytes on
+//     the partner's mbarrier, no cluster barrier.  The only coupling between trunks is clip_grad_norm_'s global norm: one
+//     8-byte st.async per CTA per step to every CTA's norm mbarrier;
+//   * the head pieces are MMA tiles too: the action head is fused into the layer-2 epilogue (a C fragment is an A fragment
+//     under a permutation of K), dHW and dH2 are 3xTF32 tiles;
+//   * each chunk arrives by TMA bulk copies (cp.async.bulk + mbarrier) issued one chunk ahead by a single thread;
 //   * weights live in shared memory for the whole launch; Adam moments and the gradient live in REGISTERS: every thread
 //     owns fixed fragments of W1/W2 plus a few scalars for all 1 600 steps, so gradients are never materialised;
 //   * the five GEMMs per chunk (X W1^T, H1 W2^T, dH2 W2, dH2^T H1, dH1^T X) run on the tensor cores as mma.sync
@@ -902,9 +906,10 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
             // reduction after the exchanges totals them together with the gradient norm
             float red[6];
 
-            // ---- (2) CTA-pair exchange through distributed shared memory: every thread stores its gradient fragments (and
-            // thread 0 the loss sums) into the partner's PAY buffer as float4 groups straight from registers, cluster
-            // barrier, add.  a + b == b + a in floating point, so both CTAs of a pair end up with bit-identical sums and
+            // ---- (2) CTA-pair exchange through distributed shared memory: every thread stores its gradient fragments and its
+            // loss partial sums into the partner's PAY buffer as float4 groups straight from registers (st.async, completing
+            // bytes on the partner's mbarrier; the W2 / head groups already left during the backward pass), waits for its own
+            // mbarrier and adds.  a + b == b + a in floating point, so both CTAs of a pair end up with bit-identical sums and
             // keep their weight copies identical.   Groups: g_w2[0..NTW2), g_w1[0..NT1), g_hw, {g_s, s0, s1, s2}, {s3, s4, -, -}
             float tot[5];                                                 // loss sums: this warp -> pair -> all ranks
 #pragma unroll
@@ -1241,7 +1246,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
             }
             ICRL_MARK(8)
 
-            // ---- global gradient norm: every CTA publishes its trunk's sum of squares through DSMEM -> cluster barrier
+            // ---- global gradient norm: every CTA publishes its trunk's sum of squares through DSMEM (st.async -> norm mbarrier)
             // epoch-level KL early stop is decided by the pi CTAs right here (they have this step's KL) and rides along
             float stop_flag = 0.f;
             if (role == 0 && working) {
