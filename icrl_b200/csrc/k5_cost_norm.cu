@@ -88,19 +88,6 @@ __device__ __forceinline__ double div_known_rcp(double a, double b, double r) {
 __device__ __forceinline__ bool significand_all_ones(double b) {
     return (__double_as_longlong(b) & 0x000fffffffffffffLL) == 0x000fffffffffffffLL;
 }
-// update_from_moments with tot = count + n and rcp = RN(1 / tot) supplied
-__device__ __forceinline__ void rms_step_rcp(double bm, double bv, double n, double tot, double rcp, double& mean,
-                                             double& var, double count) {
-    const double delta = __dsub_rn(bm, mean);
-    const double new_mean = __dadd_rn(mean, div_known_rcp(__dmul_rn(delta, n), tot, rcp));
-    const double m_a = __dmul_rn(var, count);
-    const double m_b = __dmul_rn(bv, n);
-    const double cross = div_known_rcp(__dmul_rn(__dmul_rn(__dmul_rn(delta, delta), count), n), tot, rcp);
-    const double m_2 = __dadd_rn(__dadd_rn(m_a, m_b), cross);
-    mean = new_mean;
-    var = div_known_rcp(m_2, tot, rcp);
-}
-
 // A: discounted cost return per environment.  state = {mean, var, count, cost_ret[E]} (float64).
 __global__ void cost_ret_kernel(const float* __restrict__ orig_costs, const float* __restrict__ dones,
                                 const uint8_t* __restrict__ last_dones, int T, int E, double gamma,
