@@ -199,13 +199,16 @@ int icrl_ppo_train(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* pa
  * Data-parallel K4 across the GPUs of one node (one process per GPU).  Every rank owns the rollout
  * of its own environments and runs the same persistent kernel on `batch_size` LOCAL rows per optimiser step; the
  * gradients of the three trunks are summed across ranks INSIDE the kernel: each CTA stores its gradient fragments
- * straight into every peer's receive buffer over NVLink (CUDA IPC mapped memory) as self-validating {value, sequence}
- * words (no fence, no separate flag), polls its own buffer for the peers' words and adds the partials in rank order, so all ranks apply bit-identical Adam updates and the replicated
- * parameters never drift.  The global-minibatch advantage statistics (ppo_lag.py:218-222) are data-only, so the caller
+ * straight into the peers' receive buffers over NVLink (CUDA IPC mapped memory) as self-validating 16-byte words (no
+ * fence, no separate flag), polls its own buffer and adds the contributions in rank order, so all ranks apply bit-identical
+ * Adam updates and the replicated parameters never drift.  Exchange schemes (ICRL_PPO_DIST_MODE overrides the choice):
+ * 2 / 4 ranks one-hop broadcast of {f0, f1, f2, seq ^ hash} words + rank-ordered sum; 8 ranks reduce-scatter + all-gather
+ * with the same words; other world sizes {value, seq, value, seq} words.  The three layouts share the receive buffer.
+ * The global-minibatch advantage statistics (ppo_lag.py:218-222) are data-only, so the caller
  * all-reduces one small table up front (icrl_ppo_local_advsums -> NCCL all-reduce -> icrl_ppo_dist.advsums).
  */
 #define ICRL_PPO_MAX_RANKS 8
-#define ICRL_PPO_RECV_BYTES (2 * ICRL_PPO_MAX_RANKS * 6 * 72 * 256 * 8) /* [parity][src][cta of the 6-CTA cluster][slot pair][thread] {value, seq, value, seq} */
+#define ICRL_PPO_RECV_BYTES (2 * ICRL_PPO_MAX_RANKS * 6 * 72 * 256 * 8) /* largest of the three layouts: [parity][src][cta of the 6-CTA cluster][slot pair][thread] {value, seq, value, seq} */
 #define ICRL_PPO_FLAG_BYTES (2 * ICRL_PPO_MAX_RANKS * 4 * 4)             /* [parity][src][trunk] uint32 */
 
 int icrl_comm_alloc(int64_t bytes, void** dev_ptr, unsigned char* handle64);   /* zeroed device buffer + its IPC handle */
@@ -224,8 +227,8 @@ typedef struct icrl_ppo_dist {
 
 /* local partial sums of the table above for this rank's rows (to be summed over ranks by the caller) */
 int icrl_ppo_local_advsums(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, double* advsums_out, void* stream);
-/* icrl_ppo_train with the in-kernel gradient all-reduce; per-step stats are this rank's partial sums over the GLOBAL
- * batch size (sum them over ranks); result[2] != 0 reports a peer time-out. */
+/* icrl_ppo_train with the in-kernel gradient all-reduce; the per-step stats are global already (the loss sums ride along
+ * with the gradient exchange); result[2] != 0 reports a peer time-out. */
 int icrl_ppo_train_dist(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* params, float* adam_m, float* adam_v,
                         int64_t adam_step_before, float* step_stats, int32_t* result, const icrl_ppo_dist* dist,
                         void* stream);
