@@ -224,7 +224,6 @@ class PPOLagrangian:
         for e in range(self.n_epochs):
             perms[e] = np.random.permutation(n)
             rng_states.append(np.random.get_state())
-        buf._flatten_once()          # the reference's public arrays become env-major on the first get()
 
         rename = {"log_probs": "old_log_prob", "reward_values": "old_reward_values", "cost_values": "old_cost_values"}
         data = _lib.PpoData()
@@ -237,7 +236,11 @@ class PPOLagrangian:
         perm_dev = self._stage("perm", perms)
         data.perm = perm_dev.data_ptr()
 
-        current_penalty = self.dual.nu().item()
+        # the multiplier is read on the device (no host round trip before the launch) when it lives there
+        nu_on_device = isinstance(self.dual, DualVariable)
+        if nu_on_device:
+            data.nu_device = self.dual.nu.state[4:5].data_ptr()
+        current_penalty = 0.0 if nu_on_device else float(self.dual.nu().item())
         pol = self.policy
         steps_per_epoch = (n + (self.batch_size or n) - 1) // (self.batch_size or n)
         cfg = pol.make_cfg(
@@ -254,6 +257,15 @@ class PPOLagrangian:
             _lib.check(_lib.lib().icrl_ppo_train(
                 C.byref(cfg), C.byref(data), _lib.ptr(pol._params), _lib.ptr(pol._adam_m), _lib.ptr(pol._adam_v),
                 pol.optimizer.step_count, _lib.ptr(stats), _lib.ptr(result), _lib.current_stream()))
+        # host work that does not depend on the update overlaps the kernel: the reference's public arrays become
+        # env-major on the first get() (buffers.py:594-611), and the rollout-only logger statistics
+        buf._flatten_once()
+        mean_reward_adv = np.mean(buf.reward_advantages.flatten())
+        mean_cost_adv = np.mean(buf.cost_advantages.flatten())
+        reward_ev = explained_variance(buf.reward_returns.flatten(), buf.reward_values.flatten())
+        cost_ev = explained_variance(buf.cost_returns.flatten(), buf.cost_values.flatten())
+        average_cost = np.mean(buf.orig_costs)
+        total_cost = np.sum(buf.orig_costs)
         result_h = result.cpu()                                   # synchronises
         early_stop_epoch, steps = int(result_h[0]), int(result_h[1])
         pol.optimizer.step_count += steps
@@ -270,8 +282,6 @@ class PPOLagrangian:
 
         self._n_updates += self.n_epochs
         # dual update with the original (un-normalised) cost, ppo_lag.py:301-306
-        average_cost = np.mean(buf.orig_costs)
-        total_cost = np.sum(buf.orig_costs)
         if self.update_penalty_after is None or ((self._n_updates / self.n_epochs) % self.update_penalty_after == 0):
             self.dual.update_parameter(average_cost)
 
@@ -282,12 +292,10 @@ class PPOLagrangian:
         logger.record("train/approx_kl", np.mean(last_epoch_kl))
         logger.record("train/clip_fraction", np.mean(clip_fractions.astype(np.float64)))
         logger.record("train/loss", float(last_loss))
-        logger.record("train/mean_reward_advantages", np.mean(buf.reward_advantages.flatten()))
-        logger.record("train/mean_cost_advantages", np.mean(buf.cost_advantages.flatten()))
-        logger.record("train/reward_explained_variance",
-                      explained_variance(buf.reward_returns.flatten(), buf.reward_values.flatten()))
-        logger.record("train/cost_explained_variance",
-                      explained_variance(buf.cost_returns.flatten(), buf.cost_values.flatten()))
+        logger.record("train/mean_reward_advantages", mean_reward_adv)
+        logger.record("train/mean_cost_advantages", mean_cost_adv)
+        logger.record("train/reward_explained_variance", reward_ev)
+        logger.record("train/cost_explained_variance", cost_ev)
         logger.record("train/nu", self.dual.nu().item())
         logger.record("train/nu_loss", self.dual.loss.item())
         logger.record("train/average_cost", average_cost)
