@@ -100,3 +100,34 @@ def test_readme_commands_parse_to_the_bench_workloads():
     c = utils.Config(vars(cpg_parser().parse_args(README_CPG.split())))
     assert c.cn_obs_select_dim == [0, 1] and c.cn_acs_select_dim == [-1] and c.timesteps == 1500000
     assert c.penalty_learning_rate == WORKLOADS["pointcircle"].penalty_learning_rate == 1.0
+
+
+def test_resolve_config_with_json_file_and_run_directory(tmp_path, monkeypatch):
+    """Config file < command line (icrl/icrl.py:419-447); the run directory stands in for wandb.run.dir and holds config.json."""
+    import json as _json
+    from icrl_b200.icrl import build_parser, resolve_config
+    cfg_file = tmp_path / "hc.json"
+    cfg_file.write_text(_json.dumps({"n_iters": 3, "cn_layers": [20], "train_env_id": "SynthHCWithPos-v0", "seed": 11}))
+    monkeypatch.setenv("ICRL_SAVE_ROOT", str(tmp_path / "runs"))
+    config = resolve_config(build_parser(), ["icrl", "-cf", str(cfg_file), "-ni", "5", "-bs", "128"])
+    assert config.n_iters == 5 and config.cn_layers == [20] and config.batch_size == 128 and config.seed == 11
+    assert config.train_env_id == "SynthHCWithPos-v0" and config.name.endswith("_s_11")
+    assert os.path.isdir(config.save_dir) and config.save_dir.endswith("files")
+    saved = utils.load_dict_from_json(config.save_dir, "config")
+    assert saved["n_iters"] == 5 and saved["batch_size"] == 128 and saved["save_dir"] == config.save_dir
+
+
+def test_load_expert_data_layout(tmp_path):
+    """files/EXPERT/rollouts/<i>.pkl with observations / actions / rewards (icrl/icrl.py:26-43)."""
+    import pickle
+    import numpy as np
+    from icrl_b200.icrl import load_expert_data
+    d = tmp_path / "files" / "EXPERT" / "rollouts"
+    d.mkdir(parents=True)
+    for i in range(3):
+        with open(d / f"{i}.pkl", "wb") as f:
+            pickle.dump(dict(observations=np.full((4 + i, 2), i, np.float64), actions=np.zeros((4 + i, 1), np.float32),
+                             rewards=np.array([10.0 * i]), lengths=np.array([4 + i]), save_scheme="not_airl"), f)
+    (obs, acs), mean_reward = load_expert_data(str(tmp_path), 3)
+    assert obs.shape == (15, 2) and acs.shape == (15, 1) and mean_reward == 10.0
+    assert obs[4, 0] == 1 and obs[-1, 0] == 2
