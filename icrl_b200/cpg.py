@@ -59,23 +59,10 @@ def cpg(config):
     train_env.set_cost_function(cost_function)
     eval_env.set_cost_function(cost_function)
 
-    model = PPOLagrangian(
-        policy=config.policy_name, env=train_env, algo_type='pidlagrangian' if config.use_pid else 'lagrangian',
-        learning_rate=config.learning_rate, n_steps=config.n_steps, batch_size=config.batch_size,
-        n_epochs=config.n_epochs, reward_gamma=config.reward_gamma, reward_gae_lambda=config.reward_gae_lambda,
-        cost_gamma=config.cost_gamma, cost_gae_lambda=config.cost_gae_lambda, clip_range=config.clip_range,
-        clip_range_reward_vf=config.clip_range_reward_vf, clip_range_cost_vf=config.clip_range_cost_vf,
-        ent_coef=config.ent_coef, reward_vf_coef=config.reward_vf_coef, cost_vf_coef=config.cost_vf_coef,
-        max_grad_norm=config.max_grad_norm, use_sde=config.use_sde, sde_sample_freq=config.sde_sample_freq,
-        target_kl=config.target_kl, penalty_initial_value=config.penalty_initial_value,
-        penalty_learning_rate=config.penalty_learning_rate, update_penalty_after=config.update_penalty_after,
-        budget=config.budget, seed=config.seed, device=config.device, verbose=config.verbose,
-        pid_kwargs=dict(alpha=config.budget, penalty_init=config.penalty_initial_value,
-                        Kp=config.proportional_control_coeff, Ki=config.integral_control_coeff,
-                        Kd=config.derivative_control_coeff, pid_delay=config.pid_delay,
-                        delta_p_ema_alpha=config.proportional_cost_ema_alpha,
-                        delta_d_ema_alpha=config.derivative_cost_ema_alpha),
-        policy_kwargs=dict(net_arch=utils.get_net_arch(config)))
+    from icrl_b200.icrl import ppo_lagrangian_kwargs
+    model = PPOLagrangian(env=train_env, algo_type='pidlagrangian' if config.use_pid else 'lagrangian',
+                          update_penalty_after=config.update_penalty_after, verbose=config.verbose,
+                          **ppo_lagrangian_kwargs(config))
 
     save_periodically = callbacks.CheckpointCallback(config.save_every, os.path.join(config.save_dir, "models"),
                                                      verbose=0)
@@ -96,84 +83,8 @@ def cpg(config):
 
 
 def build_parser():
-    parser = argparse.ArgumentParser()
-    parser.add_argument("file_to_run", type=str)
-    # setup
-    parser.add_argument("--config_file", "-cf", type=str, default=None)
-    parser.add_argument("--project", "-p", type=str, default="ABC")
-    parser.add_argument("--name", "-n", type=str, default=None)
-    parser.add_argument("--group", "-g", type=str, default=None)
-    parser.add_argument("--message", "-m", type=str, default=None)
-    parser.add_argument("--device", "-d", type=str, default="cpu")
-    parser.add_argument("--verbose", "-v", type=int, default=2)
-    parser.add_argument("--wandb_sweep", "-ws", type=bool, default=False)
-    parser.add_argument("--sync_wandb", "-sw", action="store_true")
-    parser.add_argument("--cost_info_str", "-cis", type=lambda x: None if str(x).lower() == "none" else str(x),
-                        default="cost")
-    # environment
-    parser.add_argument("--train_env_id", "-tei", type=str, default="HalfCheetah-v3")
-    parser.add_argument("--eval_env_id", "-eei", type=str, default="HalfCheetah-v3")
-    parser.add_argument("--dont_normalize_obs", "-dno", action="store_true")
-    parser.add_argument("--dont_normalize_reward", "-dnr", action="store_true")
-    parser.add_argument("--dont_normalize_cost", "-dnc", action="store_true")
-    parser.add_argument("--seed", "-s", type=int, default=None)
-    # networks
-    parser.add_argument("--policy_name", "-pn", type=str, default="TwoCriticsMlpPolicy")
-    parser.add_argument("--shared_layers", "-sl", type=int, default=None, nargs='*')
-    parser.add_argument("--policy_layers", "-pl", type=int, default=[64, 64], nargs='*')
-    parser.add_argument("--reward_vf_layers", "-rl", type=int, default=[64, 64], nargs='*')
-    parser.add_argument("--cost_vf_layers", "-cl", type=int, default=[64, 64], nargs='*')
-    parser.add_argument("--cnn_features_dim", "-cfd", type=int, default=512)
-    # training
-    parser.add_argument("--timesteps", "-t", type=lambda x: int(float(x)), default=1e6)
-    parser.add_argument("--n_steps", "-ns", type=int, default=2048)
-    parser.add_argument("--batch_size", "-bs", type=int, default=64)
-    parser.add_argument("--n_epochs", "-ne", type=int, default=10)
-    parser.add_argument("--num_threads", "-nt", type=int, default=5)
-    parser.add_argument("--save_every", "-se", type=float, default=5e5)
-    parser.add_argument("--eval_every", "-ee", type=float, default=2048)
-    parser.add_argument("--plot_every", "-pe", type=float, default=2048)
-    # MDP
-    parser.add_argument("--reward_gamma", "-rg", type=float, default=0.99)
-    parser.add_argument("--reward_gae_lambda", "-rgl", type=float, default=0.95)
-    parser.add_argument("--cost_gamma", "-cg", type=float, default=0.99)
-    parser.add_argument("--cost_gae_lambda", "-cgl", type=float, default=0.95)
-    # losses
-    parser.add_argument("--clip_range", "-cr", type=float, default=0.2)
-    parser.add_argument("--clip_range_reward_vf", "-crv", type=float, default=None)
-    parser.add_argument("--clip_range_cost_vf", "-ccv", type=float, default=None)
-    parser.add_argument("--ent_coef", "-ec", type=float, default=0.)
-    parser.add_argument("--reward_vf_coef", "-rvc", type=float, default=0.5)
-    parser.add_argument("--cost_vf_coef", "-cvc", type=float, default=0.5)
-    parser.add_argument("--target_kl", "-tk", type=float, default=None)
-    parser.add_argument("--max_grad_norm", "-mgn", type=float, default=0.5)
-    parser.add_argument("--learning_rate", "-lr", type=float, default=3e-4)
-    # Lagrangian
-    parser.add_argument("--use_pid", "-upid", action="store_true")
-    parser.add_argument("--penalty_initial_value", "-piv", type=float, default=1)
-    parser.add_argument("--budget", "-b", type=float, default=0.0)
-    parser.add_argument("--update_penalty_after", "-upa", type=int, default=1)
-    parser.add_argument("--proportional_control_coeff", "-kp", type=float, default=10)
-    parser.add_argument("--derivative_control_coeff", "-kd", type=float, default=0)
-    parser.add_argument("--integral_control_coeff", "-ki", type=float, default=0.0001)
-    parser.add_argument("--proportional_cost_ema_alpha", "-pema", type=float, default=0.5)
-    parser.add_argument("--derivative_cost_ema_alpha", "-dema", type=float, default=0.5)
-    parser.add_argument("--pid_delay", "-pidd", type=int, default=1)
-    parser.add_argument("--penalty_learning_rate", "-plr", type=float, default=0.1,
-                        help="Sets Learning Rate of Dual Variables if not using PID Lagrangian.")
-    # exploration
-    parser.add_argument("--use_sde", "-us", action="store_true")
-    parser.add_argument("--use_curiosity_driven_exploration", "-ucde", action="store_true")
-    parser.add_argument("--use_lambda_shaping", "-uls", action="store_true")
-    parser.add_argument("--sde_sample_freq", "-ssf", type=int, default=-1)
-    # constraint net
-    parser.add_argument("--use_null_cost", "-unc", action="store_true")
-    parser.add_argument("--cn_path", "-cp", type=str, default=None)
-    parser.add_argument('--cn_obs_select_dim', '-cosd', type=int, default=None, nargs='+')
-    parser.add_argument('--cn_acs_select_dim', '-casd', type=int, default=None, nargs='+')
-    parser.add_argument('--cn_device', '-cd', type=str, default=None)
-    parser.add_argument("--load_gail", "-lg", action="store_true")
-    return parser
+    from icrl_b200.cli import COMMON, CPG_ONLY, make_parser
+    return make_parser(COMMON, CPG_ONLY)
 
 
 def main(argv=None):

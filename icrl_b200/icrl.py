@@ -4,6 +4,7 @@ VecCostWrapper, K3, K4; `constraint_net.train` -> K2.  Plotting, video and W&B a
 and the metric table replace them)."""
 import argparse
 import importlib
+import json
 import os
 import pickle
 import sys
@@ -31,243 +32,151 @@ def load_expert_data(expert_path, num_rollouts):
     return (np.concatenate(obs, axis=0), np.concatenate(acs, axis=0)), np.mean(expert_mean_reward)
 
 
+def ppo_lagrangian_kwargs(config):
+    """Constructor arguments both drivers hand to PPOLagrangian (icrl/icrl.py:139-173, icrl/cpg.py:117-154)."""
+    kw = {k: config[k] for k in (
+        "learning_rate", "n_steps", "batch_size", "n_epochs", "reward_gamma", "reward_gae_lambda", "cost_gamma",
+        "cost_gae_lambda", "clip_range", "clip_range_reward_vf", "clip_range_cost_vf", "ent_coef", "reward_vf_coef",
+        "cost_vf_coef", "max_grad_norm", "use_sde", "sde_sample_freq", "target_kl", "penalty_initial_value",
+        "penalty_learning_rate", "budget", "seed", "device")}
+    kw["policy"] = config.policy_name
+    kw["pid_kwargs"] = dict(alpha=config.budget, penalty_init=config.penalty_initial_value,
+                            Kp=config.proportional_control_coeff, Ki=config.integral_control_coeff,
+                            Kd=config.derivative_control_coeff, pid_delay=config.pid_delay,
+                            delta_p_ema_alpha=config.proportional_cost_ema_alpha,
+                            delta_d_ema_alpha=config.derivative_cost_ema_alpha)
+    kw["policy_kwargs"] = dict(net_arch=utils.get_net_arch(config))
+    return kw
+
+
+def _say(text):
+    print(utils.colorize(text, color="green", bold=True), flush=True)
+
+
 def icrl(config):
+    """The outer loop of icrl/icrl.py:45-312: forward step (PPO-Lagrangian under the current constraint: K1 per env step or
+    per rollout, K3, K4), nominal sampling, backward step (K2), evaluation, checkpoints, metrics."""
+    norm = dict(normalize_obs=not config.dont_normalize_obs)
     train_env = utils.make_train_env(env_id=config.train_env_id, save_dir=config.save_dir, use_cost_wrapper=True,
                                      base_seed=config.seed, num_threads=config.num_threads,
-                                     normalize_obs=not config.dont_normalize_obs,
                                      normalize_reward=not config.dont_normalize_reward,
-                                     normalize_cost=not config.dont_normalize_cost,
-                                     cost_info_str=config.cost_info_str, reward_gamma=config.reward_gamma,
-                                     cost_gamma=config.cost_gamma)
-    sampling_env = utils.make_eval_env(env_id=config.train_env_id, use_cost_wrapper=False,
-                                       normalize_obs=not config.dont_normalize_obs)
-    eval_env = utils.make_eval_env(env_id=config.eval_env_id, use_cost_wrapper=False,
-                                   normalize_obs=not config.dont_normalize_obs)
+                                     normalize_cost=not config.dont_normalize_cost, cost_info_str=config.cost_info_str,
+                                     reward_gamma=config.reward_gamma, cost_gamma=config.cost_gamma, **norm)
+    sampling_env = utils.make_eval_env(env_id=config.train_env_id, use_cost_wrapper=False, **norm)   # no cost needed
+    eval_env = utils.make_eval_env(env_id=config.eval_env_id, use_cost_wrapper=False, **norm)
 
-    is_discrete = _is_discrete(train_env.action_space)
+    discrete = _is_discrete(train_env.action_space)
     obs_dim = train_env.observation_space.shape[0]
-    acs_dim = train_env.action_space.n if is_discrete else train_env.action_space.shape[0]
-    action_low = action_high = None
-    if not is_discrete:
-        action_low, action_high = sampling_env.action_space.low, sampling_env.action_space.high
+    acs_dim = train_env.action_space.n if discrete else train_env.action_space.shape[0]
+    bounds = (None, None) if discrete else (sampling_env.action_space.low, sampling_env.action_space.high)
 
-    (expert_obs, expert_acs), expert_mean_reward = load_expert_data(config.expert_path, config.expert_rollouts)
+    (expert_obs, expert_acs), _expert_reward = load_expert_data(config.expert_path, config.expert_rollouts)
     expert_agent = PPOLagrangian.load(os.path.join(config.expert_path, "files/best_model.zip"), device=config.device)
+    table = logger.HumanOutputFormat(sys.stdout)
 
-    icrl_logger = logger.HumanOutputFormat(sys.stdout)
+    def cn_lr(progress_remaining):        # annealed per ICRL iteration (icrl/icrl.py:89)
+        return config.cn_learning_rate * config.anneal_clr_by_factor ** (config.n_iters * (1 - progress_remaining))
 
-    cn_lr_schedule = lambda x: (config.anneal_clr_by_factor ** (config.n_iters * (1 - x))) * config.cn_learning_rate
+    unit_stats = (np.zeros(obs_dim), np.ones(obs_dim)) if config.cn_normalize else (None, None)
     constraint_net = ConstraintNet(
-        obs_dim, acs_dim, config.cn_layers, config.cn_batch_size, cn_lr_schedule, expert_obs, expert_acs, is_discrete,
+        obs_dim, acs_dim, config.cn_layers, config.cn_batch_size, cn_lr, expert_obs, expert_acs, discrete,
         config.cn_reg_coeff, config.cn_obs_select_dim, config.cn_acs_select_dim,
         no_importance_sampling=config.no_importance_sampling,
         per_step_importance_sampling=config.per_step_importance_sampling, clip_obs=config.clip_obs,
-        initial_obs_mean=None if not config.cn_normalize else np.zeros(obs_dim),
-        initial_obs_var=None if not config.cn_normalize else np.ones(obs_dim),
-        action_low=action_low, action_high=action_high, target_kl_old_new=config.cn_target_kl_old_new,
-        target_kl_new_old=config.cn_target_kl_new_old, train_gail_lambda=config.train_gail_lambda, eps=config.cn_eps,
-        device=config.device)
+        initial_obs_mean=unit_stats[0], initial_obs_var=unit_stats[1], action_low=bounds[0], action_high=bounds[1],
+        target_kl_old_new=config.cn_target_kl_old_new, target_kl_new_old=config.cn_target_kl_new_old,
+        train_gail_lambda=config.train_gail_lambda, eps=config.cn_eps, device=config.device)
+
     # ICRL_WHOLE_BUFFER_RELABEL=1: relabel + cost-normalise each rollout on the device after collection instead of
     # calling the cost function at every environment step (same numbers, T fewer launches per rollout)
     whole_buffer = os.environ.get("ICRL_WHOLE_BUFFER_RELABEL", "0") == "1"
-    train_env.set_cost_function(None if whole_buffer else constraint_net.cost_function)
-    true_cost_function = get_true_cost_function(config.eval_env_id)
 
-    create_nominal_agent = lambda: PPOLagrangian(
-        policy=config.policy_name, env=train_env, learning_rate=config.learning_rate, n_steps=config.n_steps,
-        batch_size=config.batch_size, n_epochs=config.n_epochs, reward_gamma=config.reward_gamma,
-        reward_gae_lambda=config.reward_gae_lambda, cost_gamma=config.cost_gamma,
-        cost_gae_lambda=config.cost_gae_lambda, clip_range=config.clip_range,
-        clip_range_reward_vf=config.clip_range_reward_vf, clip_range_cost_vf=config.clip_range_cost_vf,
-        ent_coef=config.ent_coef, reward_vf_coef=config.reward_vf_coef, cost_vf_coef=config.cost_vf_coef,
-        max_grad_norm=config.max_grad_norm, use_sde=config.use_sde, sde_sample_freq=config.sde_sample_freq,
-        target_kl=config.target_kl, penalty_initial_value=config.penalty_initial_value,
-        penalty_learning_rate=config.penalty_learning_rate, budget=config.budget, seed=config.seed,
-        device=config.device, verbose=0,
-        pid_kwargs=dict(alpha=config.budget, penalty_init=config.penalty_initial_value,
-                        Kp=config.proportional_control_coeff, Ki=config.integral_control_coeff,
-                        Kd=config.derivative_control_coeff, pid_delay=config.pid_delay,
-                        delta_p_ema_alpha=config.proportional_cost_ema_alpha,
-                        delta_d_ema_alpha=config.derivative_cost_ema_alpha),
-        policy_kwargs=dict(net_arch=utils.get_net_arch(config)))
-    nominal_agent = create_nominal_agent()
+    def plug_cost():
+        train_env.set_cost_function(None if whole_buffer else constraint_net.cost_function)
+    plug_cost()
+    true_cost = get_true_cost_function(config.eval_env_id)
 
+    def new_agent():
+        return PPOLagrangian(env=train_env, verbose=0, **ppo_lagrangian_kwargs(config))
+    agent = new_agent()
     if config.use_curiosity_driven_exploration:
         raise NotImplementedError("curiosity-driven exploration (icrl/exploration.py) is outside the hot path")
 
-    timesteps = 0.
-    if config.warmup_timesteps is not None:
-        print(utils.colorize("\nWarming up", color="green", bold=True))
-        nominal_agent.learn(total_timesteps=config.warmup_timesteps, cost_function=null_cost)
-        timesteps += nominal_agent.num_timesteps
+    total_steps = 0.
+    if config.warmup_timesteps is not None:             # no cost during warm-up
+        _say("\nWarming up")
+        agent.learn(total_timesteps=config.warmup_timesteps, cost_function=null_cost)
+        total_steps += agent.num_timesteps
 
-    start_time = time.time()
-    print(utils.colorize("\nBeginning training", color="green", bold=True), flush=True)
-    best_true_reward, best_true_cost, best_forward_kl, best_reverse_kl = -np.inf, np.inf, np.inf, np.inf
-    metrics = {}
-    for itr in range(config.n_iters):
-        if config.reset_policy and itr != 0:
-            print(utils.colorize("Resetting agent", color="green", bold=True), flush=True)
-            nominal_agent = create_nominal_agent()
-        current_progress_remaining = 1 - float(itr) / float(config.n_iters)
+    def checkpoint(folder, agent_name, cn_name, stats_name):
+        agent.save(os.path.join(folder, agent_name))
+        constraint_net.save(os.path.join(folder, cn_name))
+        if isinstance(train_env, VecNormalize):
+            train_env.save(os.path.join(folder, stats_name))
 
-        # forward step: PPO-Lagrangian on the current constraint (K1 per env step, K3 + K4 per rollout)
-        nominal_agent.learn(total_timesteps=config.forward_timesteps,
-                            cost_function=constraint_net if whole_buffer else "cost")
-        forward_metrics = dict(logger.Logger.CURRENT.name_to_value)
-        timesteps += nominal_agent.num_timesteps
+    t_start = time.time()
+    _say("\nBeginning training")
+    best = {"reward": -np.inf, "cost": np.inf, "forward_kl": np.inf, "reverse_kl": np.inf}
+    row = {}
+    for it in range(config.n_iters):
+        if it and config.reset_policy:
+            _say("Resetting agent")
+            agent = new_agent()
+        progress_remaining = 1 - float(it) / float(config.n_iters)
 
+        # ---- forward step
+        agent.learn(total_timesteps=config.forward_timesteps, cost_function=constraint_net if whole_buffer else "cost")
+        forward = dict(logger.Logger.CURRENT.name_to_value)
+        total_steps += agent.num_timesteps
+
+        # ---- nominal trajectories of the updated policy
         sync_envs_normalization(train_env, sampling_env)
-        orig_observations, observations, actions, rewards, lengths = utils.sample_from_agent(
-            nominal_agent, sampling_env, config.expert_rollouts)
+        nom_obs, _nom_obs_normalised, nom_acs, _nom_rewards, nom_lengths = utils.sample_from_agent(
+            agent, sampling_env, config.expert_rollouts)
 
-        # backward step: constraint-net update (K2)
-        mean, var = None, None
-        if config.cn_normalize:
-            mean, var = sampling_env.obs_rms.mean, sampling_env.obs_rms.var
-        backward_metrics = constraint_net.train(config.backward_iters, orig_observations, actions, lengths, mean, var,
-                                                current_progress_remaining)
-        train_env.set_cost_function(None if whole_buffer else constraint_net.cost_function)
+        # ---- backward step
+        stats = (sampling_env.obs_rms.mean, sampling_env.obs_rms.var) if config.cn_normalize else (None, None)
+        backward = constraint_net.train(config.backward_iters, nom_obs, nom_acs, nom_lengths, stats[0], stats[1],
+                                        progress_remaining)
+        plug_cost()
 
-        average_true_cost = np.mean(true_cost_function(orig_observations, actions))
-        samples_behind = np.mean(orig_observations[..., 0] < -3)
-        samples_infront = np.mean(orig_observations[..., 0] > 3)
+        # ---- evaluation: true cost of the nominal samples, reward in the true environment, KLs to the expert
+        seen = {"cost": np.mean(true_cost(nom_obs, nom_acs)),
+                "behind": np.mean(nom_obs[..., 0] < -3), "infront": np.mean(nom_obs[..., 0] > 3)}
         sync_envs_normalization(train_env, eval_env)
-        average_true_reward, std_true_reward = utils.evaluate_policy(nominal_agent, eval_env, n_eval_episodes=10,
-                                                                     deterministic=False)
-        forward_kl = utils.compute_kl(nominal_agent, expert_obs, expert_acs, expert_agent)
-        reverse_kl = utils.compute_kl(expert_agent, orig_observations, actions, nominal_agent)
+        seen["reward"], seen["reward_std"] = utils.evaluate_policy(agent, eval_env, n_eval_episodes=10, deterministic=False)
+        seen["forward_kl"] = utils.compute_kl(agent, expert_obs, expert_acs, expert_agent)
+        seen["reverse_kl"] = utils.compute_kl(expert_agent, nom_obs, nom_acs, agent)
 
-        if itr % config.save_every == 0:
-            path = os.path.join(config.save_dir, f"models/icrl_{itr}_itrs")
-            utils.del_and_make(path)
-            nominal_agent.save(os.path.join(path, "nominal_agent"))
-            constraint_net.save(os.path.join(path, "cn.pt"))
-            if isinstance(train_env, VecNormalize):
-                train_env.save(os.path.join(path, f"{itr}_train_env_stats.pkl"))
-        if average_true_reward > best_true_reward:
-            print(utils.colorize("Saving new best model", color="green", bold=True), flush=True)
-            nominal_agent.save(os.path.join(config.save_dir, "best_nominal_model"))
-            constraint_net.save(os.path.join(config.save_dir, "best_cn_model.pt"))
-            if isinstance(train_env, VecNormalize):
-                train_env.save(os.path.join(config.save_dir, "train_env_stats.pkl"))
+        # ---- checkpoints: periodic, and the best-reward model so far
+        if it % config.save_every == 0:
+            folder = os.path.join(config.save_dir, f"models/icrl_{it}_itrs")
+            utils.del_and_make(folder)
+            checkpoint(folder, "nominal_agent", "cn.pt", f"{it}_train_env_stats.pkl")
+        if seen["reward"] > best["reward"]:
+            _say("Saving new best model")
+            checkpoint(config.save_dir, "best_nominal_model", "best_cn_model.pt", "train_env_stats.pkl")
+        best["reward"] = max(best["reward"], seen["reward"])
+        for key in ("cost", "forward_kl", "reverse_kl"):
+            best[key] = min(best[key], seen[key])
 
-        best_true_reward = max(best_true_reward, average_true_reward)
-        best_true_cost = min(best_true_cost, average_true_cost)
-        best_forward_kl = min(best_forward_kl, forward_kl)
-        best_reverse_kl = min(best_reverse_kl, reverse_kl)
-
-        metrics = {
-            "time(m)": (time.time() - start_time) / 60, "iteration": itr, "timesteps": timesteps,
-            "true/reward": average_true_reward, "true/reward_std": std_true_reward, "true/cost": average_true_cost,
-            "true/samples_infront": samples_infront, "true/samples_behind": samples_behind,
-            "true/forward_kl": forward_kl, "true/reverse_kl": reverse_kl,
-            "best_true/best_reward": best_true_reward, "best_true/best_cost": best_true_cost,
-            "best_true/best_forward_kl": best_forward_kl, "best_true/best_reverse_kl": best_reverse_kl,
-        }
-        metrics.update({k.replace("train/", "forward/"): v for k, v in forward_metrics.items()})
-        metrics.update(backward_metrics)
+        row = {"time(m)": (time.time() - t_start) / 60, "iteration": it, "timesteps": total_steps,
+               "true/reward": seen["reward"], "true/reward_std": seen["reward_std"], "true/cost": seen["cost"],
+               "true/samples_infront": seen["infront"], "true/samples_behind": seen["behind"],
+               "true/forward_kl": seen["forward_kl"], "true/reverse_kl": seen["reverse_kl"]}
+        row.update({f"best_true/best_{k}": v for k, v in best.items()})
+        row.update({k.replace("train/", "forward/"): v for k, v in forward.items()})
+        row.update(backward)
         if config.verbose > 0:
-            icrl_logger.write(metrics, {k: None for k in metrics.keys()}, step=itr)
+            table.write(row, {k: None for k in row}, step=it)
         with open(os.path.join(config.save_dir, "metrics.jsonl"), "a") as f:
-            import json
-            f.write(json.dumps({k: (v.item() if hasattr(v, "item") else v) for k, v in metrics.items()},
-                               default=float) + "\n")
-    return metrics
+            f.write(json.dumps({k: (v.item() if hasattr(v, "item") else v) for k, v in row.items()}, default=float) + "\n")
+    return row
 
 
 def build_parser():
-    parser = argparse.ArgumentParser()
-    parser.add_argument("file_to_run", type=str)
-    # setup
-    parser.add_argument("--config_file", "-cf", type=str, default=None)
-    parser.add_argument("--project", "-p", type=str, default="ABC")
-    parser.add_argument("--name", "-n", type=str, default=None)
-    parser.add_argument("--group", "-g", type=str, default=None)
-    parser.add_argument("--device", "-d", type=str, default="cpu")
-    parser.add_argument("--verbose", "-v", type=int, default=2)
-    parser.add_argument("--sync_wandb", "-sw", action="store_true")
-    parser.add_argument("--wandb_sweep", "-ws", type=bool, default=False)
-    # environments
-    parser.add_argument("--train_env_id", "-tei", type=str, default="HalfCheetah-v3")
-    parser.add_argument("--eval_env_id", "-eei", type=str, default="HalfCheetah-v3")
-    parser.add_argument("--dont_normalize_obs", "-dno", action="store_true")
-    parser.add_argument("--dont_normalize_reward", "-dnr", action="store_true")
-    parser.add_argument("--dont_normalize_cost", "-dnc", action="store_true")
-    parser.add_argument("--seed", "-s", type=int, default=None)
-    parser.add_argument("--clip_obs", "-co", type=int, default=20)
-    parser.add_argument("--cost_info_str", "-cis", type=str, default="cost")
-    # networks
-    parser.add_argument("--policy_name", "-pn", type=str, default="TwoCriticsMlpPolicy")
-    parser.add_argument("--shared_layers", "-sl", type=int, default=None, nargs='*')
-    parser.add_argument("--policy_layers", "-pl", type=int, default=[64, 64], nargs='*')
-    parser.add_argument("--reward_vf_layers", "-rvl", type=int, default=[64, 64], nargs='*')
-    parser.add_argument("--cost_vf_layers", "-cvl", type=int, default=[64, 64], nargs='*')
-    # training
-    parser.add_argument("--n_steps", "-ns", type=int, default=2048)
-    parser.add_argument("--batch_size", "-bs", type=int, default=64)
-    parser.add_argument("--n_epochs", "-ne", type=int, default=10)
-    parser.add_argument("--num_threads", "-nt", type=int, default=5)
-    parser.add_argument("--save_every", "-se", type=float, default=1)
-    parser.add_argument("--eval_every", "-ee", type=float, default=2048)
-    # MDP
-    parser.add_argument("--reward_gamma", "-rg", type=float, default=0.99)
-    parser.add_argument("--reward_gae_lambda", "-rgl", type=float, default=0.95)
-    parser.add_argument("--cost_gamma", "-cg", type=float, default=0.99)
-    parser.add_argument("--cost_gae_lambda", "-cgl", type=float, default=0.95)
-    # losses
-    parser.add_argument("--clip_range", "-cr", type=float, default=0.2)
-    parser.add_argument("--clip_range_reward_vf", "-crv", type=float, default=None)
-    parser.add_argument("--clip_range_cost_vf", "-ccv", type=float, default=None)
-    parser.add_argument("--ent_coef", "-ec", type=float, default=0.)
-    parser.add_argument("--reward_vf_coef", "-rvc", type=float, default=0.5)
-    parser.add_argument("--cost_vf_coef", "-cvc", type=float, default=0.5)
-    parser.add_argument("--target_kl", "-tk", type=float, default=None)
-    parser.add_argument("--max_grad_norm", "-mgn", type=float, default=0.5)
-    parser.add_argument("--learning_rate", "-lr", type=float, default=3e-4)
-    # Lagrangian
-    parser.add_argument("--use_pid", "-upid", action="store_true")
-    parser.add_argument("--penalty_initial_value", "-piv", type=float, default=1)
-    parser.add_argument("--budget", "-b", type=float, default=0.0)
-    parser.add_argument("--update_penalty_after", "-upa", type=int, default=1)
-    parser.add_argument("--proportional_control_coeff", "-kp", type=float, default=10)
-    parser.add_argument("--derivative_control_coeff", "-kd", type=float, default=0)
-    parser.add_argument("--integral_control_coeff", "-ki", type=float, default=0.0001)
-    parser.add_argument("--proportional_cost_ema_alpha", "-pema", type=float, default=0.5)
-    parser.add_argument("--derivative_cost_ema_alpha", "-dema", type=float, default=0.5)
-    parser.add_argument("--pid_delay", "-pidd", type=int, default=1)
-    parser.add_argument("--penalty_learning_rate", "-plr", type=float, default=0.1,
-                        help="Sets Learning Rate of Dual Variables if use_pid is not true.")
-    # exploration
-    parser.add_argument("--use_sde", "-us", action="store_true")
-    parser.add_argument("--use_curiosity_driven_exploration", "-ucde", action="store_true")
-    parser.add_argument("--sde_sample_freq", "-ssf", type=int, default=-1)
-    # ICRL
-    parser.add_argument('--train_gail_lambda', '-tgl', action='store_true')
-    parser.add_argument("--n_iters", "-ni", type=int, default=100)
-    parser.add_argument("--warmup_timesteps", "-wt", type=lambda x: int(float(x)), default=None)
-    parser.add_argument("--forward_timesteps", "-ft", type=lambda x: int(float(x)), default=1e6)
-    parser.add_argument("--backward_iters", "-bi", type=int, default=10)
-    parser.add_argument('--no_importance_sampling', '-nis', action='store_true')
-    parser.add_argument('--per_step_importance_sampling', '-psis', action='store_true')
-    parser.add_argument('--reset_policy', '-rp', action='store_true')
-    # constraint net
-    parser.add_argument("--cn_layers", "-cl", type=int, default=[64, 64], nargs='*')
-    parser.add_argument("--anneal_clr_by_factor", "-aclr", type=float, default=1.0)
-    parser.add_argument("--cn_learning_rate", "-clr", type=float, default=3e-4)
-    parser.add_argument("--cn_reg_coeff", "-crc", type=float, default=0)
-    parser.add_argument("--cn_batch_size", "-cbs", type=int, default=None)
-    parser.add_argument('--cn_obs_select_dim', '-cosd', type=int, default=None, nargs='+')
-    parser.add_argument('--cn_acs_select_dim', '-casd', type=int, default=None, nargs='+')
-    parser.add_argument('--cn_plot_every', '-cpe', type=int, default=1)
-    parser.add_argument('--cn_normalize', '-cn', action='store_true')
-    parser.add_argument("--cn_target_kl_old_new", "-ctkon", type=float, default=10)
-    parser.add_argument("--cn_target_kl_new_old", "-ctkno", type=float, default=10)
-    parser.add_argument("--cn_eps", "-ce", type=float, default=1e-5)
-    # expert data
-    parser.add_argument('--expert_path', '-ep', type=str, default='icrl/expert_data/HCWithPos-vm0')
-    parser.add_argument('--expert_rollouts', '-er', type=int, default=20)
-    return parser
+    from icrl_b200.cli import COMMON, ICRL_ONLY, make_parser
+    return make_parser(COMMON, ICRL_ONLY)
 
 
 def resolve_config(parser, argv):

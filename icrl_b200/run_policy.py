@@ -46,21 +46,8 @@ def run_policy(args):
 
 
 def main(argv=None):
-    parser = argparse.ArgumentParser()
-    parser.add_argument("file_to_run", type=str)
-    parser.add_argument("--load_dir", "-l", type=str, default="icrl/wandb/latest-run/")
-    parser.add_argument("--is_icrl", "-ii", action='store_true')
-    parser.add_argument("--remote", "-r", action="store_true")
-    parser.add_argument("--save_dir", "-s", type=str, default="run_policy")
-    parser.add_argument("--env_id", "-e", type=str, default=None)
-    parser.add_argument("--load_itr", "-li", type=int, default=None)
-    parser.add_argument("--n_rollouts", "-nr", type=int, default=3)
-    parser.add_argument("--dont_make_video", "-dmv", action="store_true")
-    parser.add_argument("--dont_save_trajs", "-dst", action="store_true")
-    parser.add_argument("--save_using_airl_scheme", "-suas", action="store_true")
-    parser.add_argument("--reward_threshold", "-rt", type=float, default=None)
-    parser.add_argument("--length_threshold", "-lt", type=int, default=None)
-    args = parser.parse_args(sys.argv[1:] if argv is None else argv)
+    from icrl_b200.cli import RUN_POLICY, make_parser
+    args = make_parser(RUN_POLICY).parse_args(sys.argv[1:] if argv is None else argv)
     if args.remote or args.save_using_airl_scheme:
         raise NotImplementedError("W&B restore and the AIRL save scheme are outside the ICRL hot path")
     run_policy(args)

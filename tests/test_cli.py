@@ -13,14 +13,15 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 def _parser(name):
     if name == "icrl":
         from icrl_b200.icrl import build_parser
-    elif name == "cpg":
+        return build_parser()
+    if name == "cpg":
         from icrl_b200.cpg import build_parser
-    else:
-        pytest.skip("run_policy builds its parser inside main()")
-    return build_parser()
+        return build_parser()
+    from icrl_b200.cli import RUN_POLICY, make_parser
+    return make_parser(RUN_POLICY)
 
 
-@pytest.mark.parametrize("name", ["icrl", "cpg"])
+@pytest.mark.parametrize("name", ["icrl", "cpg", "run_policy"])
 def test_flags_match_reference(name):
     ref = json.load(open(os.path.join(GOLD, f"flags_{name}.json")))
     parser = _parser(name)
@@ -38,15 +39,6 @@ def test_flags_match_reference(name):
             assert a.nargs == flag["nargs"], key
         if flag.get("type") in ("int", "float", "str", "bool"):
             assert a.type.__name__ == flag["type"], key
-
-
-def test_run_policy_flags_match_reference():
-    import inspect
-    from icrl_b200 import run_policy
-    src = inspect.getsource(run_policy.main)
-    for flag in json.load(open(os.path.join(GOLD, "flags_run_policy.json"))):
-        for o in flag["opts"]:
-            assert f'"{o}"' in src, o
 
 
 def test_merge_priority_cli_over_file_over_default():
