@@ -129,12 +129,23 @@ def get_net_arch(config):
 
 
 # ---------------------------------------------------------------- environments (icrl/utils.py:247-303)
+def set_random_seed(seed: int) -> None:
+    """stable_baselines3/common/utils.py:23-40: python, numpy and torch global generators."""
+    import random
+    random.seed(seed)
+    np.random.seed(seed)
+    th.manual_seed(seed)
+
+
 def make_env(env_id, rank, log_dir, seed=0):
     def _init():
         env = _envs.make(env_id)
         if hasattr(env, "seed"):
             env.seed(seed + rank)
         return env
+    # like the reference (icrl/utils.py:247-256) building the factory seeds the GLOBAL generators: this is what makes the
+    # constraint net's initial weights (created right after the environments) a function of --seed
+    set_random_seed(seed)
     return _init
 
 

@@ -72,6 +72,16 @@ def test_run_me_cpg_run_policy_icrl(tmp_path):
     assert os.path.exists(os.path.join(icrl_dir, "best_cn_model.pt"))
     assert os.path.exists(os.path.join(icrl_dir, "models", "icrl_1_itrs", "nominal_agent.zip"))
     assert "Beginning training" in out
+    # 4. the same ICRL run with whole-rollout relabelling on the device (K1 + K5 after collection instead of one cost call
+    #    per environment step): identical seeds -> identical learned costs, so the metrics of iteration 0 agree
+    env_wb = dict(env, ICRL_WHOLE_BUFFER_RELABEL="1")
+    _run(["icrl"] + common + ["-ep", run_dir, "-er", "3", "-ft", "2048", "-ni", "1", "-bi", "3", "-cl", "20", "-clr", "0.05", "-crc",
+                              "0.5", "-aclr", "0.9", "-psis", "-ctkno", "2.5", "-tk", "0.01"], env_wb)
+    dirs = sorted(d for d in glob.glob(str(tmp_path / "runs" / "*" / "files")) if os.path.dirname(d) != run_dir)
+    wb_dir = [d for d in dirs if d != icrl_dir][0]
+    wb_row = json.loads(open(os.path.join(wb_dir, "metrics.jsonl")).readline())
+    for k in ("forward/average_cost", "forward/nu", "backward/cn_loss", "true/cost"):
+        assert np.isclose(wb_row[k], rows[0][k], rtol=1e-5, atol=1e-7), (k, wb_row[k], rows[0][k])
 
 
 def test_run_me_cpg_with_frozen_constraint_net_and_gail(tmp_path):
