@@ -8,6 +8,7 @@ stop.  The dual step (dual_variable.py:47-57) follows as a second tiny launch.  
 keep the reference's control flow; env stepping stays on the host (north_star (c)).
 """
 import ctypes as C
+from collections import deque
 import os
 import time
 from typing import Any, Callable, Dict, Optional, Union
@@ -323,6 +324,8 @@ class PPOLagrangian:
     def _setup_learn(self, total_timesteps, callback, reset_num_timesteps=True):
         """base_class.py:479-538 (without eval-env / Monitor plumbing)."""
         self.start_time = time.time()
+        if self.ep_info_buffer is None or reset_num_timesteps:      # base_class.py:503-507
+            self.ep_info_buffer = deque(maxlen=100)
         if reset_num_timesteps:
             self.num_timesteps = 0
         else:
@@ -362,6 +365,9 @@ class PPOLagrangian:
                 costs = cost_function(orig_obs.copy(), clipped_actions)
                 orig_costs = costs
             self.num_timesteps += env.num_envs
+            for info in infos:                                        # base_class.py:368-389 (Monitor's episode summaries)
+                if info.get("episode") is not None:
+                    self.ep_info_buffer.extend([info["episode"]])
             callback.update_locals(locals())
             if callback.on_step() is False:
                 return False
@@ -384,18 +390,33 @@ class PPOLagrangian:
         iteration = 0
         total_timesteps, callback = self._setup_learn(total_timesteps, callback, reset_num_timesteps)
         callback.on_training_start(locals(), globals())
+
+        def training_infos(itr):
+            elapsed = max(time.time() - self.start_time, 1e-9)
+            logger.record("time/iterations", itr, exclude="tensorboard")
+            logger.record("time/fps", int(self.num_timesteps / elapsed))
+            logger.record("time/time_elapsed", int(elapsed), exclude="tensorboard")
+            logger.record("time/total_timesteps", self.num_timesteps, exclude="tensorboard")
+            if len(self.ep_info_buffer) > 0 and len(self.ep_info_buffer[0]) > 0:
+                extra = {key for ep in self.ep_info_buffer for key in ep} - {'r', 'l', 't'}
+                for key in extra:
+                    vals = [ep[key] for ep in self.ep_info_buffer]
+                    logger.record(f"rollout/ep_{key}_mean", np.mean(vals))
+                    logger.record(f"rollout/ep_{key}_max", np.max(vals))
+                    logger.record(f"rollout/ep_{key}_min", np.min(vals))
+                logger.record("rollout/ep_rew_mean", np.mean([ep["r"] for ep in self.ep_info_buffer]))
+                logger.record("rollout/ep_len_mean", np.mean([ep["l"] for ep in self.ep_info_buffer]))
+
         while self.num_timesteps < total_timesteps:
             if self.collect_rollouts(self.env, callback, self.rollout_buffer, self.n_steps, cost_function) is False:
                 break
             iteration += 1
             self._update_current_progress_remaining(self.num_timesteps, total_timesteps)
             if log_interval is not None and iteration % log_interval == 0:
-                fps = int(self.num_timesteps / max(time.time() - self.start_time, 1e-9))
-                logger.record("time/iterations", iteration, exclude="tensorboard")
-                logger.record("time/fps", fps)
-                logger.record("time/total_timesteps", self.num_timesteps, exclude="tensorboard")
+                training_infos(iteration)
                 logger.dump(step=self.num_timesteps)
             self.train()
+        training_infos(iteration + 1)          # like the reference: left in the logger for the caller (forward/* metrics)
         callback.on_training_end()
         return self
 

@@ -15,6 +15,7 @@ that ``VecCostWrapper`` can hand each step's (previous obs, action) batch to ``C
 Environment simulation itself stays on the host: it is not part of the hot path.
 """
 import pickle
+import time
 from copy import deepcopy
 from typing import Callable, List, Optional, Sequence
 
@@ -70,16 +71,25 @@ class DummyVecEnv(VecEnv):
         env = self.envs[0]
         super().__init__(len(self.envs), env.observation_space, env.action_space)
         self.actions = None
+        # episode accounting of the reference's Monitor wrapper (common/monitor.py): raw reward sum / length / wall time
+        self._t_start = time.time()
+        self._ep_rew = [0.0] * self.num_envs
+        self._ep_len = [0] * self.num_envs
 
     def step_async(self, actions):
         self.actions = actions
 
     def step_wait(self):
         obs, rews, dones, infos = [], [], [], []
-        for env, a in zip(self.envs, self.actions):
+        for i, (env, a) in enumerate(zip(self.envs, self.actions)):
             o, r, d, info = env.step(a)
             info = dict(info)
+            self._ep_rew[i] += float(r)
+            self._ep_len[i] += 1
             if d:
+                info["episode"] = {"r": round(self._ep_rew[i], 6), "l": self._ep_len[i],
+                                   "t": round(time.time() - self._t_start, 6)}
+                self._ep_rew[i], self._ep_len[i] = 0.0, 0
                 info["terminal_observation"] = o
                 o = env.reset()
             obs.append(o), rews.append(r), dones.append(d), infos.append(info)
@@ -87,6 +97,7 @@ class DummyVecEnv(VecEnv):
                 infos)
 
     def reset(self):
+        self._ep_rew, self._ep_len = [0.0] * self.num_envs, [0] * self.num_envs
         return np.stack([env.reset() for env in self.envs]).astype(np.float32)
 
     def seed(self, seed: Optional[int] = None):

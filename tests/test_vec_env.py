@@ -99,3 +99,21 @@ def test_synthetic_envs_shapes():
     assert g.reset().shape == (1,) and g.action_space.n == 2
     with pytest.raises(ImportError):
         envs.make("HCWithPos-v0")
+
+
+def test_dummy_vec_env_reports_episode_summaries():
+    """The reference wraps every env in Monitor: at episode end info['episode'] = {r: raw reward sum, l: length, t: time}."""
+    env = vec_env.DummyVecEnv([lambda: ScriptedEnv(21), lambda: ScriptedEnv(22)])
+    env.reset()
+    acc, n, seen = [0.0, 0.0], [0, 0], 0
+    for _ in range(200):
+        _, rews, dones, infos = env.step(np.zeros((2, 2), np.float32))
+        for i in range(2):
+            acc[i] += float(rews[i]); n[i] += 1
+            if dones[i]:
+                ep = infos[i]["episode"]
+                assert ep["l"] == n[i] and abs(ep["r"] - acc[i]) < 1e-4 and ep["t"] >= 0 and "terminal_observation" in infos[i]
+                acc[i], n[i], seen = 0.0, 0, seen + 1
+            else:
+                assert "episode" not in infos[i]
+    assert seen > 5
