@@ -3,7 +3,8 @@
 
 Run in the build container only (needs /root/reference):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py            # everything: k1 k2 k3 k4 venv flags ckpt gail
+    python tests/golden/make_golden.py venv gail  # or a subset
 
 Outputs are small .npz files committed next to this script; the tests (CPU and GPU) read
 only those, never the reference.  torch 2.11.0 / numpy 2.3.5 CPU, torch.set_num_threads(1)
@@ -409,6 +410,6 @@ def golden_gail():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["k1", "k2", "k3", "k4"]
+    which = sys.argv[1:] or ["k1", "k2", "k3", "k4", "venv", "flags", "ckpt", "gail"]
     for w in which:
         globals()[f"golden_{w}"]()
