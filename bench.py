@@ -27,7 +27,12 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch as th  # noqa: E402
 
-METRIC = "learner transitions/sec per ICRL iteration"
+METRIC = "learner transitions/sec per ICRL iteration at 1/2/4/8 B200 vs host CPU"     # BASELINE.json's metric, verbatim
+try:
+    with open(os.path.join(ROOT, "BASELINE.json")) as _f:
+        METRIC = json.load(_f).get("metric", METRIC)
+except (OSError, ValueError):
+    pass
 UNIT = "transitions/s"
 
 
