@@ -64,3 +64,89 @@ def test_advsums_allreduce_gloo_world2(tmp_path):
                         "127.0.0.1", "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+# ------------------------------------------------------------------------------------------- K2 sharding blueprint
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("per_step", [True, False])
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_constraint_net_update_equals_single_process(world, per_step):
+    """oracle/cn_dp.py (episodes sharded over ranks, two all-reduces per Adam step) reproduces oracle/cn.py::train."""
+    import numpy as np
+    import torch as th
+    from oracle import cn as ocn, cn_dp
+    rng = np.random.default_rng(5)
+    lengths = [30, 41, 25, 50, 37, 44, 29]
+    n = sum(lengths)
+    nom_obs, nom_acs = rng.standard_normal((n, 18)) * 3, rng.standard_normal((n, 6)).astype(np.float32)
+    exp_obs, exp_acs = rng.standard_normal((150, 18)) * 3, rng.standard_normal((150, 6)).astype(np.float32)
+    spec = ocn.CNSpec(18, 6, (20,), False, clip_obs=20., regularizer_coeff=0.5, per_step_importance_sampling=per_step,
+                      target_kl_old_new=10, target_kl_new_old=10)
+    th.manual_seed(0)
+    dims = [spec.input_dims, 20, 1]
+    params = []
+    for i in range(2):
+        lin = th.nn.Linear(dims[i], dims[i + 1])
+        params += [lin.weight.detach().clone(), lin.bias.detach().clone()]
+    single = [p.clone() for p in params]
+    m1 = ocn.train(single, ocn.adam_init(single), spec, 4, nom_obs, nom_acs, lengths, exp_obs, exp_acs, lr=0.01)
+    reps, ms = cn_dp.train_simulated(world, params, spec, 4, nom_obs, nom_acs, lengths, exp_obs, exp_acs, lr=0.01)
+    for r in range(world):
+        for a, b in zip(reps[r], single):
+            assert th.allclose(a, b, rtol=2e-5, atol=2e-7), float((a - b).abs().max())
+        for a, b in zip(reps[r], reps[0]):
+            assert th.equal(a, b)                       # replicas stay bit identical
+        for k in ("backward/cn_loss", "backward/kl_old_new", "backward/kl_new_old", "backward/is_max", "backward/is_min"):
+            assert abs(ms[r][k] - m1[k]) <= 1e-4 * max(1.0, abs(m1[k])), (k, ms[r][k], m1[k])
+    covered = cn_dp.shard_episodes(lengths, world)
+    assert covered[0][0] == 0 and covered[-1][1] == len(lengths) and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+
+
+def test_sharded_constraint_net_update_gloo_world2(tmp_path):
+    """The same blueprint over real collectives: two gloo processes, torch.distributed all_reduce (sum / min / max)."""
+    script = tmp_path / "k2.py"
+    script.write_text(textwrap.dedent('''
+        import sys, numpy as np, torch as th, torch.distributed as dist
+        sys.path.insert(0, %r)
+        from oracle import cn as ocn, cn_dp
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        th.set_num_threads(1)
+        rng = np.random.default_rng(5)
+        lengths = [30, 41, 25, 50, 37, 44]
+        n = sum(lengths)
+        nom_obs, nom_acs = rng.standard_normal((n, 18)) * 3, rng.standard_normal((n, 6)).astype(np.float32)
+        exp_obs, exp_acs = rng.standard_normal((120, 18)) * 3, rng.standard_normal((120, 6)).astype(np.float32)
+        spec = ocn.CNSpec(18, 6, (20,), False, clip_obs=20., regularizer_coeff=0.5, per_step_importance_sampling=True,
+                          target_kl_old_new=10, target_kl_new_old=10)
+        th.manual_seed(0)
+        params = []
+        for a, b in ((spec.input_dims, 20), (20, 1)):
+            lin = th.nn.Linear(a, b)
+            params += [lin.weight.detach().clone(), lin.bias.detach().clone()]
+        single = [p.clone() for p in params]
+        ocn.train(single, ocn.adam_init(single), spec, 3, nom_obs, nom_acs, lengths, exp_obs, exp_acs, lr=0.01)
+
+        def reduce(op):
+            def run(t):
+                t = t.clone()
+                dist.all_reduce(t, op=op)
+                return t
+            return run
+        e0, e1, r0, r1 = cn_dp.shard_episodes(lengths, world)[rank]
+        x0, x1 = 120 * rank // world, 120 * (rank + 1) // world
+        mine = [p.clone() for p in params]
+        cn_dp.train_rank(mine, ocn.adam_init(mine), spec, 3, nom_obs[r0:r1], nom_acs[r0:r1], lengths[e0:e1], exp_obs[x0:x1],
+                         exp_acs[x0:x1], 0.01, reduce(dist.ReduceOp.SUM), reduce(dist.ReduceOp.MIN), reduce(dist.ReduceOp.MAX))
+        for a, b in zip(mine, single):
+            assert th.allclose(a, b, rtol=2e-5, atol=2e-7), float((a - b).abs().max())
+        dist.destroy_process_group()
+        print("ok", rank)
+    ''' % ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29534", str(script)], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2
