@@ -49,7 +49,8 @@ def cpg(config):
         action_low = action_high = None
         if not is_discrete:
             action_low, action_high = train_env.action_space.low, train_env.action_space.high
-        # NB: keyword call, so the reference's positional-shift quirk in ConstraintNet.load is not triggered here
+        # ConstraintNet.load reproduces the reference's positional-argument shift INSIDE load() (constraint_net.py:394-399):
+        # the loaded net neither clips observations nor actions, whatever is passed here
         constraint_net = ConstraintNet.load(config.cn_path, obs_dim=obs_dim, acs_dim=acs_dim, is_discrete=is_discrete,
                                             obs_select_dim=config.cn_obs_select_dim,
                                             acs_select_dim=config.cn_acs_select_dim, clip_obs=None, obs_mean=None,

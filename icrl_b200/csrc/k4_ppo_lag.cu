@@ -1370,9 +1370,10 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
     if (crank == 0 && tid == 0) {
         a.result[0] = early_stop_epoch;
         a.result[1] = step;
-        a.result[2] = (XCH[31] != 0.f) ? 1 : 0;   // a peer timed out in data-parallel mode
-        a.result[3] = 0;
     }
+    // an exchange wait of ANY CTA hit its bound (lost cluster peer / data-parallel rank): the host zeroes result[2] before the
+    // launch and raises when it comes back set (the parameters of such a launch are not valid)
+    if (tid == 0 && *(volatile float*)&XCH[31] != 0.f) a.result[2] = 1;
     cluster_sync_all();   // nobody exits while a peer may still address its shared memory
 }
 
@@ -1457,6 +1458,7 @@ static int ppo_train_impl(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, fl
         a.dist_mode = m ? atoi(m) : 0;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    ICRL_CUDA(cudaMemsetAsync(result, 0, 4 * sizeof(int32_t), st));
     {
         const int total_steps = a.n_epochs * a.steps_per_epoch;
         const long long n_rows = (long long)a.n_epochs * a.N, n_alloc = n_rows + icrl::RB;

@@ -17,25 +17,34 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches += n; }
 
+// Everything cached here is keyed by the CURRENT device: the API allows one object per device (cpg passes --cn_device to
+// ConstraintNet.load and --device to PPOLagrangian; every call site runs under th.cuda.device(obj_dev)).
+constexpr int kMaxDevices = 16;
+static int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+    return dev;
+}
+
 int sm_count() {
-    static int cached = -1;
-    if (cached < 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    static int cached[kMaxDevices] = {0};
+    const int dev = current_device();
+    if (cached[dev] <= 0) {
+        int n = 0;
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 148;
-        cached = n;
+        cached[dev] = n;
     }
-    return cached;
+    return cached[dev];
 }
 
 struct Scratch {
     void* ptr = nullptr;
     size_t cap = 0;
 };
-static Scratch g_dev[SLOT_COUNT], g_pin[SLOT_COUNT];
+static Scratch g_dev[kMaxDevices][SLOT_COUNT], g_pin[kMaxDevices][SLOT_COUNT];
 
 int device_scratch(Slot s, size_t bytes, void** ptr) {
-    Scratch& b = g_dev[s];
+    Scratch& b = g_dev[current_device()][s];
     if (bytes > b.cap) {
         if (b.ptr) {
             ICRL_CUDA(cudaDeviceSynchronize());
@@ -52,7 +61,7 @@ int device_scratch(Slot s, size_t bytes, void** ptr) {
 }
 
 int pinned_scratch(Slot s, size_t bytes, void** ptr) {
-    Scratch& b = g_pin[s];
+    Scratch& b = g_pin[current_device()][s];
     if (bytes > b.cap) {
         if (b.ptr) {
             ICRL_CUDA(cudaDeviceSynchronize());

@@ -88,7 +88,11 @@ def icrl(config):
         train_gail_lambda=config.train_gail_lambda, eps=config.cn_eps, device=config.device)
 
     # ICRL_WHOLE_BUFFER_RELABEL=1: relabel + cost-normalise each rollout on the device after collection instead of
-    # calling the cost function at every environment step (same numbers, T fewer launches per rollout)
+    # calling the cost function at every environment step (T fewer launches per rollout).  The costs, cost advantages
+    # and cost_rms / cost_ret statistics are bit-identical to the per-step path (tests/test_drivers_gpu.py); what
+    # differs: callbacks see all-zero `costs` / `orig_costs` in update_locals() at every step (the buffer is filled
+    # after collection), and info['cost'] is absent.  During warm-up (null_cost) the per-step wrapper stays plugged in,
+    # as in the reference, so that cost_rms keeps seeing constraint-net costs.
     whole_buffer = os.environ.get("ICRL_WHOLE_BUFFER_RELABEL", "0") == "1"
 
     def plug_cost():
@@ -105,7 +109,11 @@ def icrl(config):
     total_steps = 0.
     if config.warmup_timesteps is not None:             # no cost during warm-up
         _say("\nWarming up")
+        # the reference's wrapper keeps calling the constraint net during warm-up (vec_cost_wrapper.py:62) and
+        # VecNormalizeWithCost keeps updating cost_rms from it: same here in both relabel modes
+        train_env.set_cost_function(constraint_net.cost_function)
         agent.learn(total_timesteps=config.warmup_timesteps, cost_function=null_cost)
+        plug_cost()
         total_steps += agent.num_timesteps
 
     def checkpoint(folder, agent_name, cn_name, stats_name):

@@ -270,6 +270,16 @@ class DeviceLearner:
         if w.backward_iters > 0 and w.nominal_rows > 0:
             self._cn_train_device()
 
+    def check(self):
+        """Synchronises and raises if any K4 launch of the last run() reported an exchange time-out (result[2])."""
+        res = self.result.cpu().numpy()
+        if (res[:, 2] != 0).any():
+            raise _lib.IcrlError(f"PPO kernel exchange time-out in rollouts {np.nonzero(res[:, 2])[0].tolist()}: the "
+                                 "replicated parameters are no longer valid")
+        want = self.steps_taken_per_rollout()
+        if (res[:, 1] != want).any():
+            raise _lib.IcrlError(f"PPO kernel took {res[:, 1].tolist()} optimiser steps, expected {want} per rollout")
+
     def steps_taken_per_rollout(self):
         full = self.w.n_epochs * self.steps_per_epoch
         return min(full, self.max_steps) if self.max_steps > 0 else full

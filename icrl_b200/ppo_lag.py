@@ -58,7 +58,10 @@ class _CallbackList(_NullCallback):
     def on_training_start(self, l, g): [c.on_training_start(l, g) for c in self.callbacks]
     def on_rollout_start(self): [c.on_rollout_start() for c in self.callbacks]
     def update_locals(self, l): [c.update_locals(l) for c in self.callbacks if hasattr(c, "update_locals")]
-    def on_step(self): return all(c.on_step() is not False for c in self.callbacks)
+    def on_step(self):
+        # callbacks.py:186-193: every callback runs (no short circuit), the results are and-ed
+        results = [c.on_step() for c in self.callbacks]
+        return all(r is not False for r in results)
     def on_rollout_end(self): [c.on_rollout_end() for c in self.callbacks]
     def on_training_end(self): [c.on_training_end() for c in self.callbacks]
 
@@ -138,8 +141,11 @@ class PPOLagrangian:
         self.rollout_buffer = None
         self.ep_info_buffer = None
         self._staging = {}
+        self.comm = None                # data-parallel plumbing (icrl_b200.distributed.PpoComm), see enable_data_parallel()
         if _init_setup_model:
             self._setup_model()
+        if os.environ.get("ICRL_DATA_PARALLEL", "0") == "1":
+            self.enable_data_parallel()
 
     # ---------------------------------------------------------------- setup (on_policy_algorithm.py:316-338, ppo_lag.py:145-175)
     def set_random_seed(self, seed: Optional[int] = None) -> None:
@@ -181,6 +187,23 @@ class PPOLagrangian:
                 if isinstance(v, (float, int)):
                     assert v > 0, "`clip_range_vf` must be positive, pass `None` to deactivate vf clipping"
                 setattr(self, name, get_schedule_fn(v))
+
+    def enable_data_parallel(self, comm=None) -> "PPOLagrangian":
+        """Data-parallel train() across the GPUs of one node (not in the reference, which has no
+        distributed path).  One process per GPU under torch.distributed: every rank collects rollouts from ITS OWN
+        `n_envs` environments, and train() runs `batch_size` local rows per optimiser step with the gradient all-reduce
+        fused into the persistent kernel over NVLink peer memory (global minibatch = world x batch_size).  Parameters
+        must start replicated (same seed / checkpoint on every rank); they stay bit-identical afterwards.  Also switched
+        on by ICRL_DATA_PARALLEL=1 when the process group is initialised (`torchrun ... run_me.py icrl ...`)."""
+        import torch.distributed as dist
+        if comm is None:
+            if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+                return self
+            from .distributed import PpoComm
+            with th.cuda.device(self.device):
+                comm = PpoComm()
+        self.comm = comm
+        return self
 
     def _update_learning_rate(self, optimizer) -> None:
         """base_class.py:213-227."""
@@ -254,10 +277,24 @@ class PPOLagrangian:
             max_steps=int(getattr(self, "_max_steps", 0)))
         stats = th.zeros(self.n_epochs * steps_per_epoch, _lib.PPO_STATS_PER_STEP, device=self.device)
         result = th.zeros(4, dtype=th.int32, device=self.device)
+        dp = self.comm is not None and self.comm.world > 1
         with th.cuda.device(self.device):
-            _lib.check(_lib.lib().icrl_ppo_train(
-                C.byref(cfg), C.byref(data), _lib.ptr(pol._params), _lib.ptr(pol._adam_m), _lib.ptr(pol._adam_v),
-                pol.optimizer.step_count, _lib.ptr(stats), _lib.ptr(result), _lib.current_stream()))
+            if not dp:
+                _lib.check(_lib.lib().icrl_ppo_train(
+                    C.byref(cfg), C.byref(data), _lib.ptr(pol._params), _lib.ptr(pol._adam_m), _lib.ptr(pol._adam_v),
+                    pol.optimizer.step_count, _lib.ptr(stats), _lib.ptr(result), _lib.current_stream()))
+            else:
+                # the advantage statistics of ppo_lag.py:218-222 are those of the GLOBAL minibatch: local partial sums ->
+                # one small all-reduce; the gradients (and the loss sums) are all-reduced inside the kernel
+                advsums = th.zeros(self.n_epochs * steps_per_epoch, 4, dtype=th.float64, device=self.device)
+                _lib.check(_lib.lib().icrl_ppo_local_advsums(C.byref(cfg), C.byref(data), _lib.ptr(advsums),
+                                                              _lib.current_stream()))
+                self.comm.all_reduce_sum(advsums)
+                desc = self.comm.descriptor(advsums)
+                keep.append(advsums)
+                _lib.check(_lib.lib().icrl_ppo_train_dist(
+                    C.byref(cfg), C.byref(data), _lib.ptr(pol._params), _lib.ptr(pol._adam_m), _lib.ptr(pol._adam_v),
+                    pol.optimizer.step_count, _lib.ptr(stats), _lib.ptr(result), C.byref(desc), _lib.current_stream()))
         # host work that does not depend on the update overlaps the kernel: the reference's public arrays become
         # env-major on the first get() (buffers.py:594-611), and the rollout-only logger statistics
         buf._flatten_once()
@@ -267,8 +304,19 @@ class PPOLagrangian:
         cost_ev = explained_variance(buf.cost_returns.flatten(), buf.cost_values.flatten())
         average_cost = np.mean(buf.orig_costs)
         total_cost = np.sum(buf.orig_costs)
+        if dp:      # the dual step sees the mean cost over every rank's environments
+            tot = th.tensor([float(np.sum(buf.orig_costs, dtype=np.float64)), float(buf.orig_costs.size)],
+                            dtype=th.float64, device=self.device)
+            self.comm.all_reduce_sum(tot)
+            tot = tot.cpu()
+            average_cost, total_cost = float(tot[0] / tot[1]), float(tot[0])
         result_h = result.cpu()                                   # synchronises
         early_stop_epoch, steps = int(result_h[0]), int(result_h[1])
+        if int(result_h[2]) != 0:
+            raise _lib.IcrlError("PPO kernel: an exchange wait timed out (a cluster peer or a data-parallel rank did not "
+                                 "deliver its gradients); the parameters of this launch are not valid")
+        if dp:
+            self.comm.advance(steps)
         pol.optimizer.step_count += steps
         epochs_run = min(self.n_epochs, early_stop_epoch + 1)
         np.random.set_state(rng_states[epochs_run - 1])
@@ -365,12 +413,12 @@ class PPOLagrangian:
                 costs = cost_function(orig_obs.copy(), clipped_actions)
                 orig_costs = costs
             self.num_timesteps += env.num_envs
-            for info in infos:                                        # base_class.py:368-389 (Monitor's episode summaries)
-                if info.get("episode") is not None:
-                    self.ep_info_buffer.extend([info["episode"]])
             callback.update_locals(locals())
             if callback.on_step() is False:
                 return False
+            for info in infos:                  # on_policy_algorithm.py:404 -> base_class.py:368-389, after on_step
+                if info.get("episode") is not None:
+                    self.ep_info_buffer.extend([info["episode"]])
             n_steps += 1
             if discrete:
                 actions = actions.reshape(-1, 1)

@@ -14,8 +14,13 @@ def _run(args, env=None):
     return r.stdout
 
 
+def _have_ref():
+    return os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "stable_baselines3", "__init__.py"))
+
+
 def test_reference_arm_line():
-    out = _run(["--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-steps", "12"])
+    """kind "reference" (the unmodified reference from baseline/_ref) when that copy exists, the oracle port otherwise."""
+    out = _run(["--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-steps", "12", "--ref-budget", "6"])
     lines = [l for l in out.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
@@ -23,7 +28,9 @@ def test_reference_arm_line():
     assert d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1
     assert d["config"]["workload"].startswith("HalfCheetah")
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "K4" in cb["sample"]
+    assert cb["kind"] == ("reference" if _have_ref() else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and "K4" in cb["sample"]
+    assert set(d["config"]) >= {"workload", "batch_size", "n_epochs", "rollouts", "n_steps", "parallelism"}
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and d["vs_baseline"] is None
 
