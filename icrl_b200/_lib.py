@@ -9,6 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libicrl_b200.so")
 
+ABI_VERSION = 2
 MAX_SELECT, MAX_HIDDEN, CN_MAX_WIDTH = 512, 3, 64
 PPO_STATS_PER_STEP = 8
 
@@ -31,7 +32,14 @@ class CnTrainCfg(C.Structure):
         ("train_gail_lambda", C.c_int32), ("eps", C.c_float), ("regularizer_coeff", C.c_float),
         ("target_kl_old_new", C.c_float), ("target_kl_new_old", C.c_float), ("lr", C.c_double),
         ("adam_beta1", C.c_double), ("adam_beta2", C.c_double), ("adam_eps", C.c_double),
+        ("batch_size", C.c_int32), ("perm", c_void),
     ]
+
+
+class CnDist(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("recv", c_void * 8), ("buffer_bytes", C.c_int64),
+                ("seq_base", C.c_uint32), ("n_nominal_global", C.c_int64), ("n_expert_global", C.c_int64),
+                ("n_episodes_global", C.c_int32), ("episode_base", C.c_int32)]
 
 
 class CnTrainMetrics(C.Structure):
@@ -82,6 +90,10 @@ SIGNATURES = {
     "icrl_cn_train": (C.c_int, [C.POINTER(CnDesc), C.POINTER(CnTrainCfg), c_void, C.c_int32, c_void, C.c_int64, c_void,
                                 C.c_int32, c_void, C.c_int32, c_void, C.c_int64, c_void, c_void, C.POINTER(C.c_int64),
                                 C.POINTER(CnTrainMetrics), c_void]),
+    "icrl_cn_dist_bytes": (C.c_int64, [C.POINTER(CnDesc), C.c_int32]),
+    "icrl_cn_train_dist": (C.c_int, [C.POINTER(CnDesc), C.POINTER(CnTrainCfg), c_void, C.c_int32, c_void, C.c_int64, c_void,
+                                     C.c_int32, c_void, C.c_int32, c_void, C.c_int64, c_void, c_void, C.POINTER(C.c_int64),
+                                     C.POINTER(CnTrainMetrics), C.POINTER(CnDist), c_void]),
     "icrl_dual_gae": (C.c_int, [c_void] * 8 + [C.c_int32, C.c_int32] + [C.c_double] * 4 + [c_void] * 5),
     "icrl_dual_gae_host": (C.c_int, [c_void] * 8 + [C.c_int32, C.c_int32] + [C.c_double] * 4 + [c_void] * 5),
     "icrl_ppo_param_count": (C.c_int64, [C.POINTER(PpoCfg)]),
@@ -119,7 +131,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.icrl_abi_version() != 1:
+        if handle.icrl_abi_version() != ABI_VERSION:
             raise IcrlError("ABI version mismatch between icrl_b200/_lib.py and libicrl_b200.so")
         _lib = handle
     return _lib

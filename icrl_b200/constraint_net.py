@@ -305,8 +305,6 @@ class ConstraintNet:
     ) -> Dict[str, Any]:
         """constraint_net.py:137-229 (full-batch mode).  One C-ABI call runs all `iterations` Adam steps on the
         device, with IS weights, both KLs and the early-stop test evaluated there; returns the backward/* metrics."""
-        if self.batch_size is not None:
-            raise NotImplementedError("cn_batch_size: the shipped configs and the CUDA path use full batches (None)")
         self._update_learning_rate(current_progress_remaining)
         self.current_obs_mean, self.current_obs_var = obs_mean, obs_var
         no, na, _ = self._host_inputs(nominal_obs, nominal_acs)
@@ -321,22 +319,50 @@ class ConstraintNet:
         assert int(lengths.sum()) == no.shape[0] or not self.importance_sampling, "episode_lengths must cover nominal_obs"
         no_dev, na_dev = th.from_numpy(no).to(self._dev), th.from_numpy(na).to(self._dev)
         off_dev = th.from_numpy(offsets).to(self._dev)
+        comm = getattr(self, "comm", None)
+        dp = comm is not None and comm.world > 1
+        if dp:          # this rank's slice of the (replicated) expert batch; the nominal episodes are this rank's own
+            n_exp = eo_dev.shape[0]
+            lo, hi = n_exp * comm.rank // comm.world, n_exp * (comm.rank + 1) // comm.world
+            eo_dev, ea_dev = eo_dev[lo:hi], ea_dev[lo:hi]
+        # minibatch mode (constraint_net.py:304-317): one numpy permutation of min(N_nominal, N_expert) per backward
+        # iteration that runs; all are drawn up front and the RNG is rewound to where the reference would have left it
+        perm_dev, rng_states = None, None
+        if self.batch_size is not None:
+            if dp:
+                raise NotImplementedError("cn_batch_size is not available in data-parallel mode")
+            size = min(no.shape[0], eo_dev.shape[0])
+            perms, rng_states = np.empty((max(int(iterations), 1), size), dtype=np.int32), [np.random.get_state()]
+            for i in range(int(iterations)):
+                perms[i] = np.random.permutation(size)
+                rng_states.append(np.random.get_state())
+            perm_dev = th.from_numpy(perms).to(self._dev)
         g = self.optimizer.param_groups[0]
         cfg = _lib.CnTrainCfg(
             iterations=int(iterations), importance_sampling=int(self.importance_sampling),
             per_step_is=int(self.per_step_importance_sampling), train_gail_lambda=int(bool(self.train_gail_lambda)),
             eps=float(self.eps), regularizer_coeff=float(self.regularizer_coeff or 0.0),
             target_kl_old_new=float(self.target_kl_old_new), target_kl_new_old=float(self.target_kl_new_old),
-            lr=float(g["lr"]), adam_beta1=float(g["betas"][0]), adam_beta2=float(g["betas"][1]), adam_eps=float(g["eps"]))
+            lr=float(g["lr"]), adam_beta1=float(g["betas"][0]), adam_beta2=float(g["betas"][1]), adam_eps=float(g["eps"]),
+            batch_size=0 if perm_dev is None else max(1, min(int(self.batch_size), perm_dev.shape[1])),
+            perm=None if perm_dev is None else perm_dev.data_ptr())
         metrics = _lib.CnTrainMetrics()
         step = C.c_int64(self.optimizer.step_count)
-        with th.cuda.device(self._dev):
-            _lib.check(_lib.lib().icrl_cn_train(
-                C.byref(self._get_desc()), C.byref(cfg), _lib.ptr(no_dev), int(no.dtype == np.float64), _lib.ptr(na_dev),
+        args = (C.byref(self._get_desc()), C.byref(cfg), _lib.ptr(no_dev), int(no.dtype == np.float64), _lib.ptr(na_dev),
                 no.shape[0], _lib.ptr(off_dev), len(lengths), _lib.ptr(eo_dev), int(eo_dev.dtype == th.float64),
                 _lib.ptr(ea_dev), eo_dev.shape[0], _lib.ptr(self._adam_m), _lib.ptr(self._adam_v), C.byref(step),
-                C.byref(metrics), _lib.current_stream()))
+                C.byref(metrics))
+        with th.cuda.device(self._dev):
+            if not dp:
+                _lib.check(_lib.lib().icrl_cn_train(*args, _lib.current_stream()))
+            else:
+                shapes = comm.shapes(no.shape[0], eo_dev.shape[0], len(lengths), self._dev)
+                dist_desc = comm.descriptor(*shapes)
+                _lib.check(_lib.lib().icrl_cn_train_dist(*args, C.byref(dist_desc), _lib.current_stream()))
+                comm.advance(int(iterations))
         self.optimizer.step_count = int(step.value)
+        if rng_states is not None:      # permutations are only drawn in iterations that get past the KL test
+            np.random.set_state(rng_states[min(int(metrics.early_stop_itr), int(iterations))])
         keys = ("cn_loss", "expert_loss", "unweighted_nominal_loss", "nominal_loss", "regularizer_loss", "is_mean",
                 "is_max", "is_min", "nominal_preds_max", "nominal_preds_min", "nominal_preds_mean", "expert_preds_max",
                 "expert_preds_min", "expert_preds_mean")
@@ -345,6 +371,21 @@ class ConstraintNet:
             out.update({"backward/kl_old_new": float(metrics.kl_old_new), "backward/kl_new_old": float(metrics.kl_new_old),
                         "backward/early_stop_itr": int(metrics.early_stop_itr)})
         return out
+
+    def enable_data_parallel(self, comm=None, max_episodes: int = 65536) -> "ConstraintNet":
+        """Data-parallel train() across the GPUs of one node (the reference has no distributed path): one
+        process per GPU under torch.distributed, every rank passes the nominal episodes IT sampled to train(), the expert
+        batch is split evenly by rank, and the partial sums of every backward iteration are exchanged inside the kernels
+        over NVLink peer memory.  Parameters must start replicated; they stay bit-identical."""
+        import torch.distributed as dist
+        if comm is None:
+            if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+                return self
+            from .distributed import CnComm
+            with th.cuda.device(self._dev):
+                comm = CnComm(self._get_desc(), max_episodes)
+        self.comm = comm
+        return self
 
     # ---------------------------------------------------------------- checkpoints (constraint_net.py:323-402)
     def save(self, save_path):

@@ -27,10 +27,11 @@
 extern "C" {
 #endif
 
-#define ICRL_ABI_VERSION 1
+#define ICRL_ABI_VERSION 2
 
 #define ICRL_EINVAL (-1)      /* bad argument (message in icrl_last_error) */
 #define ICRL_EUNSUPPORTED (-2) /* shape outside what the kernels were built for */
+#define ICRL_EPEER (-3)        /* data-parallel mode: a peer rank did not deliver its part of an exchange in time */
 
 #define ICRL_MAX_SELECT 512   /* max len(select_dim) of a constraint net */
 #define ICRL_MAX_HIDDEN 3     /* max number of hidden layers of a constraint net */
@@ -84,8 +85,10 @@ int icrl_cn_forward_host(const icrl_cn_desc* d, const void* obs, int32_t obs_is_
                          int64_t n_rows, float* out, int32_t out_kind, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * K2 -- replaces ConstraintNet.train + compute_is_weights + th.optim.Adam.step
- * (constraint_net.py:137-256) with batch_size=None (full batch, the only mode the shipped configs use).
+ * K2 -- replaces ConstraintNet.train + compute_is_weights + ConstraintNet.get + th.optim.Adam.step
+ * (constraint_net.py:137-256, 301-317): full batch (batch_size None, what the shipped configs use) or minibatches
+ * (`-cbs`): one numpy permutation of min(n_nominal, n_expert) per backward iteration, the SAME batch indices into the
+ * nominal and the expert set, one Adam step per minibatch, importance weights from the full nominal set.
  */
 typedef struct icrl_cn_train_cfg {
     int32_t iterations;              /* backward_iters */
@@ -98,6 +101,9 @@ typedef struct icrl_cn_train_cfg {
     float target_kl_new_old;         /* -1 disables */
     double lr;                       /* already evaluated lr_schedule(progress) */
     double adam_beta1, adam_beta2, adam_eps;
+    int32_t batch_size;              /* 0: full batch (cn_batch_size None); > 0: minibatch size (constraint_net.py:304-317) */
+    const int32_t* perm;             /* batch_size > 0: device int32 [iterations][min(n_nominal, n_expert)], the permutations
+                                        numpy would draw (constraint_net.py:306) -- generated by the host so seeds stay compatible */
 } icrl_cn_train_cfg;
 
 /* metrics written by icrl_cn_train (host struct), the `backward/ *` keys of constraint_net.py:209-227 */
@@ -121,6 +127,29 @@ int icrl_cn_train(const icrl_cn_desc* d, const icrl_cn_train_cfg* cfg,
                   const void* expert_obs, int32_t expert_obs_is_f64, const float* expert_acs, int64_t n_expert,
                   float* adam_m, float* adam_v, int64_t* adam_step,
                   icrl_cn_train_metrics* metrics, void* stream);
+
+/* Data-parallel K2 across the GPUs of one node ("shard nominal rows by whole episodes and expert rows
+ * evenly").  Every rank passes ITS nominal episodes / expert rows to the same call; the partial sums of the three reductions of
+ * a backward iteration (sum of IS ratios + per-episode products; sum / max / min of the weights; gradient + loss sums) are
+ * stored by the kernels straight into every rank's exchange buffer (icrl_comm_alloc'ed, CUDA-IPC mapped, NVLink peer stores),
+ * published with a per-exchange sequence flag and summed in rank order by the consuming kernel, so all replicas apply
+ * bit-identical Adam steps.  No host synchronisation inside, no NCCL.  Returns ICRL_EPEER when a peer did not deliver within
+ * ~2 s.  Minibatch mode is not available here (ICRL_EUNSUPPORTED). */
+typedef struct icrl_cn_dist {
+    int32_t rank, world;
+    void* recv[8];                   /* recv[r]: rank r's exchange buffer (>= icrl_cn_dist_bytes), recv[rank] is local; zeroed at allocation */
+    int64_t buffer_bytes;            /* size of each exchange buffer */
+    uint32_t seq_base;               /* every rank advances it by iterations + 1 after each call */
+    int64_t n_nominal_global, n_expert_global;   /* row counts over all ranks (the loss means divide by these) */
+    int32_t n_episodes_global, episode_base;     /* episodes over all ranks; global index of this rank's first episode */
+} icrl_cn_dist;
+int64_t icrl_cn_dist_bytes(const icrl_cn_desc* d, int32_t n_episodes_global);
+int icrl_cn_train_dist(const icrl_cn_desc* d, const icrl_cn_train_cfg* cfg,
+                       const void* nominal_obs, int32_t nominal_obs_is_f64, const float* nominal_acs, int64_t n_nominal,
+                       const int32_t* episode_offsets, int32_t n_episodes,
+                       const void* expert_obs, int32_t expert_obs_is_f64, const float* expert_acs, int64_t n_expert,
+                       float* adam_m, float* adam_v, int64_t* adam_step,
+                       icrl_cn_train_metrics* metrics, const icrl_cn_dist* dist, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K3 -- replaces RolloutBufferWithCost.compute_returns_and_advantage (both calls of

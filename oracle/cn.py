@@ -150,9 +150,23 @@ def adam_step(params, grads, state, lr, eps=1e-5, betas=(0.9, 0.999)):
             p.addcdiv_(m, denom, value=-step_size)
 
 
+def batches(batch_size, nom_size, exp_size):
+    """constraint_net.py:301-317 `get`: everything when batch_size is None, else one numpy permutation (global RNG) of
+    min(nom_size, exp_size) cut into minibatches -- the SAME indices for the nominal and the expert set."""
+    if batch_size is None:
+        yield None, None
+        return
+    size = min(nom_size, exp_size)
+    indices = np.random.permutation(size)
+    for start in range(0, size, batch_size):
+        yield indices[start:start + batch_size], indices[start:start + batch_size]
+
+
 def train(params, adam_state, spec: CNSpec, iterations: int, nominal_obs, nominal_acs, episode_lengths,
-          expert_obs, expert_acs, lr: float, adam_eps: float = 1e-5, materialize_broadcast: bool = False):
-    """constraint_net.py:137-229 with batch_size=None (the only mode the shipped configs use).
+          expert_obs, expert_acs, lr: float, adam_eps: float = 1e-5, materialize_broadcast: bool = False,
+          batch_size: Optional[int] = None):
+    """constraint_net.py:137-229; batch_size=None is the full-batch mode the shipped configs use, an int the -cbs
+    minibatch mode (permutations from the global numpy RNG, as the reference draws them).
 
     `spec.obs_mean/obs_var` must already hold this call's normalisation stats (:152-153).
     Quirk A: in per-step IS mode the reference multiplies an [N,1,1] weight
@@ -184,27 +198,29 @@ def train(params, adam_state, spec: CNSpec, iterations: int, nominal_obs, nomina
                 break
         else:
             is_weights = th.ones(nominal.shape[0])
-        is_batch = is_weights[..., None]
-
-        nominal_preds = forward(params, nominal)
-        expert_preds = forward(params, expert)
-        if spec.train_gail_lambda:                                    # :193-197
-            bce = th.nn.BCELoss()
-            nominal_loss = bce(nominal_preds, th.zeros(*nominal_preds.size()))
-            expert_loss = bce(expert_preds, th.ones(*expert_preds.size()))
-            regularizer_loss = th.tensor(0)
-            loss = nominal_loss + expert_loss
-        else:                                                         # :199-202
-            expert_loss = th.mean(th.log(expert_preds + eps))
-            log_nom = th.log(nominal_preds + eps)
-            if is_batch.dim() == 3 and not materialize_broadcast:
-                nominal_loss = th.mean(is_batch) * th.mean(log_nom)
-            else:
-                nominal_loss = th.mean(is_batch * log_nom)
-            regularizer_loss = spec.regularizer_coeff * (th.mean(1 - expert_preds) + th.mean(1 - nominal_preds))
-            loss = (-expert_loss + nominal_loss) + regularizer_loss
-        grads = th.autograd.grad(loss, params)
-        adam_step(params, grads, adam_state, lr, eps=adam_eps)
+        for nom_idx, exp_idx in batches(batch_size, nominal.shape[0], expert.shape[0]):      # :180-207
+            nominal_batch = nominal if nom_idx is None else nominal[nom_idx]
+            expert_batch = expert if exp_idx is None else expert[exp_idx]
+            is_batch = (is_weights if nom_idx is None else is_weights[nom_idx])[..., None]
+            nominal_preds = forward(params, nominal_batch)
+            expert_preds = forward(params, expert_batch)
+            if spec.train_gail_lambda:                                    # :193-197
+                bce = th.nn.BCELoss()
+                nominal_loss = bce(nominal_preds, th.zeros(*nominal_preds.size()))
+                expert_loss = bce(expert_preds, th.ones(*expert_preds.size()))
+                regularizer_loss = th.tensor(0)
+                loss = nominal_loss + expert_loss
+            else:                                                         # :199-202
+                expert_loss = th.mean(th.log(expert_preds + eps))
+                log_nom = th.log(nominal_preds + eps)
+                if is_batch.dim() == 3 and not materialize_broadcast:
+                    nominal_loss = th.mean(is_batch) * th.mean(log_nom)
+                else:
+                    nominal_loss = th.mean(is_batch * log_nom)
+                regularizer_loss = spec.regularizer_coeff * (th.mean(1 - expert_preds) + th.mean(1 - nominal_preds))
+                loss = (-expert_loss + nominal_loss) + regularizer_loss
+            grads = th.autograd.grad(loss, params)
+            adam_step(params, grads, adam_state, lr, eps=adam_eps)
 
     for p in params:
         p.requires_grad_(False)

@@ -3,7 +3,7 @@
 
 Run in the build container only (needs /root/reference):
 
-    python tests/golden/make_golden.py            # everything: k1 k2 k3 k4 venv flags ckpt gail
+    python tests/golden/make_golden.py            # everything: k1 k2 k2x k3 k4 k4x venv flags ckpt gail
     python tests/golden/make_golden.py venv gail  # or a subset
 
 Outputs are small .npz files committed next to this script; the tests (CPU and GPU) read
@@ -65,7 +65,8 @@ def synth_obs_acs(rng, n, obs_dim, acs_dim, is_discrete, obs_dtype=np.float64):
 
 
 def make_cn(shape, seed, *, normalize=False, clip_obs=20., reg=0.0, no_is=False, per_step=False,
-            expert=None, tkon=-1, tkno=-1, lr=3e-3, obs_select=None, acs_select=None, rng=None):
+            expert=None, tkon=-1, tkno=-1, lr=3e-3, obs_select=None, acs_select=None, rng=None, batch_size=None,
+            gail=False):
     th.manual_seed(seed)
     s = SHAPES[shape]
     low = high = None
@@ -77,10 +78,10 @@ def make_cn(shape, seed, *, normalize=False, clip_obs=20., reg=0.0, no_is=False,
         var = rng.uniform(0.3, 9.0, size=s["obs_dim"])
     eo, ea = expert if expert is not None else (None, None)
     return ConstraintNet(
-        s["obs_dim"], s["acs_dim"], s["hidden"], None, lambda x: lr, eo, ea, s["is_discrete"], reg,
+        s["obs_dim"], s["acs_dim"], s["hidden"], batch_size, lambda x: lr, eo, ea, s["is_discrete"], reg,
         obs_select, acs_select, no_importance_sampling=no_is, per_step_importance_sampling=per_step,
         clip_obs=clip_obs, initial_obs_mean=mean, initial_obs_var=var, action_low=low, action_high=high,
-        target_kl_old_new=tkon, target_kl_new_old=tkno, eps=1e-5, device="cpu")
+        target_kl_old_new=tkon, target_kl_new_old=tkno, train_gail_lambda=gail, eps=1e-5, device="cpu")
 
 
 def golden_k1():
@@ -185,6 +186,46 @@ def golden_k2():
                 break
         save(f"k2_{name}", **arrays)
 
+
+
+def golden_k2x():
+    """Round-2 additions: the --train_gail_lambda BCE variant (constraint_net.py:193-197) and the -cbs minibatch mode
+    (constraint_net.py:304-317; numpy permutation per backward iteration, seed stored)."""
+    rng = np.random.default_rng(199)
+    cases = {
+        # name: shape, episode lengths, n_expert, kwargs, iters
+        "hc_gail": ("hc", [70, 50, 60], 200, dict(gail=True, lr=0.01, tkno=10, tkon=10), 4),
+        "ant_gail_nois": ("ant", [90, 70], 150, dict(gail=True, no_is=True, lr=0.003), 3),
+        "hc_mb_perstep": ("hc", [50, 60, 40], 140, dict(per_step=True, reg=0.5, tkno=2.5, tkon=10, lr=0.001, batch_size=64), 3),
+        "hc_mb_perepisode": ("hc", [50, 60, 40, 30], 150, dict(reg=0.2, tkno=10, tkon=10, lr=0.0005, batch_size=48), 3),
+        "lgw_mb_big": ("lgw", [40, 35, 50], 160, dict(lr=0.003, clip_obs=20., batch_size=500), 3),   # one minibatch per iteration
+        "hc_mb_earlystop": ("hc", [60, 50, 40], 120, dict(tkno=1e-4, tkon=10, lr=0.05, batch_size=50), 6),
+    }
+    for name, (shape, lengths, n_exp, kw, iters) in cases.items():
+        s = SHAPES[shape]
+        n_nom = int(np.sum(lengths))
+        eo, ea = synth_obs_acs(rng, n_exp, s["obs_dim"], s["acs_dim"], s["is_discrete"])
+        no, na = synth_obs_acs(rng, n_nom, s["obs_dim"], s["acs_dim"], s["is_discrete"])
+        no = no * 1.5 + 0.5
+        cn = make_cn(shape, seed=7, expert=(eo, ea), rng=rng, **kw)
+        arrays = dict(expert_obs=eo, expert_acs=ea, nominal_obs=no, nominal_acs=na, lengths=np.array(lengths),
+                      iters=np.array(iters), lr=np.array(kw["lr"]), reg=np.array(kw.get("reg", 0.0)),
+                      per_step=np.array(kw.get("per_step", False)), no_is=np.array(kw.get("no_is", False)),
+                      tkon=np.array(kw.get("tkon", -1.0)), tkno=np.array(kw.get("tkno", -1.0)),
+                      gail=np.array(kw.get("gail", False)), batch_size=np.array(kw.get("batch_size", 0)),
+                      numpy_seed=np.array(321))
+        arrays.update(sd_arrays("p0.", cn.network.state_dict()))
+        np.random.seed(321)
+        for call in (1, 2):
+            m = cn.train(iters, no, na, np.array(lengths), None, None, 1.0)
+            arrays.update(sd_arrays(f"p{call}.", cn.network.state_dict()))
+            arrays.update({f"m{call}.{k}": np.asarray(v, dtype=np.float64) for k, v in m.items()})
+            arrays.update({f"c{call}.{k}": v for k, v in opt_arrays(cn).items()})
+            arrays[f"rng_probe{call}"] = np.array(np.random.get_state()[1][:4].astype(np.int64))   # where the global RNG stands
+            arrays[f"rng_pos{call}"] = np.array(np.random.get_state()[2])
+            if name == "hc_mb_earlystop":
+                break
+        save(f"k2_{name}", **arrays)
 
 # ------------------------------------------------------------------------------------------- K3
 
@@ -298,6 +339,85 @@ def golden_k4():
         save(f"k4_{name}", **arrays)
 
 
+
+def k4x_inputs(seed, T, E, obs_dim, acs_dim, is_discrete):
+    """Seeded (obs, actions, rewards-like scalars) of the round-2 K4 fixtures; tests/helpers.py regenerates the SAME arrays
+    (numpy Generator streams are stable), so only the torch-dependent arrays and the outputs are stored."""
+    rng = np.random.default_rng(seed)
+    n = T * E
+    scale = rng.uniform(0.5, 8.0, size=obs_dim)
+    obs = np.clip((rng.standard_normal((n, obs_dim)) * scale).astype(np.float32) / 4.0, -10, 10).astype(np.float32)
+    acs = (rng.integers(0, acs_dim, size=(n, 1)).astype(np.float32) if is_discrete
+           else rng.standard_normal((n, acs_dim)).astype(np.float32))
+    rewards = np.abs(rng.standard_normal((T, E))).astype(np.float32)
+    costs = (np.abs(rng.standard_normal((T, E))) * 0.2).astype(np.float32)
+    dones = (rng.random((T, E)) < 0.02).astype(np.float32)
+    lp_noise = (0.05 * rng.standard_normal((T, E))).astype(np.float32)
+    last_dones = rng.random(E) < 0.3
+    return obs, acs, rewards, costs, dones, lp_noise, last_dones
+
+
+def golden_k4x():
+    """Round-2 K4 fixtures: the full-size HalfCheetah train() (2048 x 5, batch 64, 10 epochs = 1 600 dependent optimiser
+    steps: drift over a whole launch) and the large-batch regime (batch >= 2048: the many-cluster kernel)."""
+    cases = {
+        # name: shape, T, E, batch, epochs, trains, kwargs
+        "hc_full": ("hc", 2048, 5, 64, 10, 1, dict()),
+        "hc_wide": ("hc", 1024, 8, 4096, 3, 2, dict(target_kl=0.05)),
+        "ant_wide_ragged": ("ant", 512, 8, 3000, 3, 2, dict(learning_rate=3e-5, clip_range=0.4, penalty_initial_value=0.1,
+                                                            penalty_learning_rate=0.05)),
+        "lgw_wide": ("lgw", 1024, 4, 2048, 2, 1, dict(ent_coef=0.01)),
+        "hc_wide_fullbatch": ("hc", 1024, 8, None, 2, 1, dict(clip_range_reward_vf=0.2)),
+    }
+    for ci, (name, (shape, T, E, bs, ne, trains, kw)) in enumerate(cases.items()):
+        s = SHAPES[shape]
+        seed = 7000 + ci
+        env = DummyVecEnv([lambda s=s: FakeEnv(s["obs_dim"], s["acs_dim"], s["is_discrete"]) for _ in range(E)])
+        th.manual_seed(5)
+        algo = PPOLagrangian("TwoCriticsMlpPolicy", env, n_steps=T, batch_size=bs, n_epochs=ne, seed=3, device="cpu", **kw)
+        pol, buf = algo.policy, algo.rollout_buffer
+        obs, acs, rewards, costs, dones, lp_noise, last_dones = k4x_inputs(seed, T, E, s["obs_dim"], s["acs_dim"], s["is_discrete"])
+        buf.observations[:] = obs.reshape(T, E, -1)
+        buf.orig_observations[:] = obs.reshape(T, E, -1) * 2
+        buf.actions[:] = acs.reshape(T, E, -1)
+        buf.rewards[:], buf.costs[:], buf.orig_costs[:], buf.dones[:] = rewards, costs, costs, dones
+        with th.no_grad():
+            a = th.tensor(acs).long().flatten() if s["is_discrete"] else th.tensor(acs)
+            v, cv, lp, _ = pol.evaluate_actions(th.tensor(obs), a)
+        buf.reward_values[:] = v.numpy().reshape(T, E)
+        buf.cost_values[:] = cv.numpy().reshape(T, E)
+        buf.log_probs[:] = lp.numpy().reshape(T, E) + lp_noise
+        buf.full, buf.pos = True, T
+        buf.compute_returns_and_advantage(v[-E:], cv[-E:], dones=last_dones)
+        arrays = {f"buf.{k}": getattr(buf, k).copy() for k in (
+            "log_probs", "reward_values", "reward_advantages", "reward_returns", "cost_values", "cost_advantages",
+            "cost_returns")}
+        arrays["input_seed"] = np.array(seed)
+        arrays["obs_sum"] = np.array(np.float64(obs.astype(np.float64).sum()))        # guards the regenerated inputs
+        arrays["acs_sum"] = np.array(np.float64(acs.astype(np.float64).sum()))
+        arrays.update(sd_arrays("p0.", pol.state_dict()))
+        arrays["param_order"] = np.array([n for n, _ in pol.named_parameters()])
+        arrays["log_nu0"] = algo.dual.nu.log_nu.detach().numpy().copy()
+        logger.configure(folder=None, format_strings=[])
+        algo._current_progress_remaining = 1.0
+        np.random.seed(17)
+        for call in range(1, trains + 1):
+            algo.train()
+            arrays.update(sd_arrays(f"p{call}.", pol.state_dict()))
+            arrays[f"log_nu{call}"] = algo.dual.nu.log_nu.detach().numpy().copy()
+            if call == 1:
+                arrays.update({f"log.{k}": np.asarray(v, dtype=np.float64)
+                               for k, v in logger.Logger.CURRENT.name_to_value.items()})
+        hp = dict(batch_size=-1 if bs is None else bs, n_epochs=ne, numpy_seed=17, T=T, E=E, trains=trains,
+                  learning_rate=kw.get("learning_rate", 3e-4), clip_range=kw.get("clip_range", 0.2),
+                  target_kl=kw.get("target_kl", -1.0), ent_coef=kw.get("ent_coef", 0.0),
+                  penalty_initial_value=kw.get("penalty_initial_value", 1.0),
+                  penalty_learning_rate=kw.get("penalty_learning_rate", 0.01),
+                  clip_range_reward_vf=kw.get("clip_range_reward_vf", -1.0),
+                  clip_range_cost_vf=kw.get("clip_range_cost_vf", -1.0))
+        arrays.update({f"hp.{k}": np.asarray(v, dtype=np.float64) for k, v in hp.items()})
+        save(f"k4x_{name}", **arrays)
+
 # ------------------------------------------------------------------------------------------- VecEnv wrappers
 def golden_venv():
     """Reference VecCostWrapper + VecNormalizeWithCost driven by the scripted env (tests/golden/scripted_env.py)."""
@@ -410,6 +530,6 @@ def golden_gail():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["k1", "k2", "k3", "k4", "venv", "flags", "ckpt", "gail"]
+    which = sys.argv[1:] or ["k1", "k2", "k2x", "k3", "k4", "k4x", "venv", "flags", "ckpt", "gail"]
     for w in which:
         globals()[f"golden_{w}"]()

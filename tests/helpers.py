@@ -56,3 +56,36 @@ def max_param_err(pa, pb):
         a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
         worst = max(worst, float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-3)))
     return worst
+
+
+def k4x_inputs(seed, T, E, obs_dim, acs_dim, is_discrete):
+    """The seeded inputs of the round-2 K4 fixtures (tests/golden/make_golden.py::k4x_inputs, same generator calls in the
+    same order): only torch-dependent arrays and outputs are stored in the .npz files."""
+    rng = np.random.default_rng(seed)
+    n = T * E
+    scale = rng.uniform(0.5, 8.0, size=obs_dim)
+    obs = np.clip((rng.standard_normal((n, obs_dim)) * scale).astype(np.float32) / 4.0, -10, 10).astype(np.float32)
+    acs = (rng.integers(0, acs_dim, size=(n, 1)).astype(np.float32) if is_discrete
+           else rng.standard_normal((n, acs_dim)).astype(np.float32))
+    rewards = np.abs(rng.standard_normal((T, E))).astype(np.float32)
+    costs = (np.abs(rng.standard_normal((T, E))) * 0.2).astype(np.float32)
+    dones = (rng.random((T, E)) < 0.02).astype(np.float32)
+    lp_noise = (0.05 * rng.standard_normal((T, E))).astype(np.float32)
+    last_dones = rng.random(E) < 0.3
+    return obs, acs, rewards, costs, dones, lp_noise, last_dones
+
+
+def load_k4x(name):
+    """A k4x_* fixture completed with its regenerated inputs, in the key layout of the k4_* fixtures."""
+    import os
+    from conftest import GOLDEN
+    d = dict(np.load(os.path.join(GOLDEN, f"k4x_{name}.npz"), allow_pickle=False))
+    s = SHAPES[name.split("_")[0]]
+    T, E = int(d["hp.T"]), int(d["hp.E"])
+    obs, acs, _, costs, _, _, _ = k4x_inputs(int(d["input_seed"]), T, E, s["obs_dim"], s["acs_dim"], s["is_discrete"])
+    assert float(obs.astype(np.float64).sum()) == float(d["obs_sum"]) and \
+        float(acs.astype(np.float64).sum()) == float(d["acs_sum"]), "numpy Generator stream changed: regenerate k4x fixtures"
+    d["buf.observations"] = obs.reshape(T, E, -1)
+    d["buf.actions"] = acs.reshape(T, E, -1)
+    d["buf.orig_costs"] = costs
+    return d

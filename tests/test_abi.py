@@ -39,20 +39,23 @@ def test_struct_layouts_match_the_header(lib, tmp_path):
     """Compile a tiny C program against the header and compare sizeof/offsetof with the ctypes mirror."""
     from icrl_b200 import _lib
     probe = tmp_path / "probe.c"
-    probe.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "icrl_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+    probe.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "icrl_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                      'sizeof(icrl_cn_desc), offsetof(icrl_cn_desc, params), sizeof(icrl_cn_train_cfg), offsetof(icrl_cn_train_cfg, lr),'
-                     'sizeof(icrl_cn_train_metrics), sizeof(icrl_ppo_cfg), offsetof(icrl_ppo_cfg, lr), sizeof(icrl_ppo_data));return 0;}\n')
+                     'sizeof(icrl_cn_train_metrics), sizeof(icrl_ppo_cfg), offsetof(icrl_ppo_cfg, lr), sizeof(icrl_ppo_data),'
+                     'offsetof(icrl_cn_train_cfg, perm), sizeof(icrl_cn_dist), offsetof(icrl_cn_dist, episode_base),'
+                     'sizeof(icrl_ppo_dist));return 0;}\n')
     exe = tmp_path / "probe"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(probe), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [C.sizeof(_lib.CnDesc), _lib.CnDesc.params.offset, C.sizeof(_lib.CnTrainCfg), _lib.CnTrainCfg.lr.offset,
-            C.sizeof(_lib.CnTrainMetrics), C.sizeof(_lib.PpoCfg), _lib.PpoCfg.lr.offset, C.sizeof(_lib.PpoData)]
+            C.sizeof(_lib.CnTrainMetrics), C.sizeof(_lib.PpoCfg), _lib.PpoCfg.lr.offset, C.sizeof(_lib.PpoData),
+            _lib.CnTrainCfg.perm.offset, C.sizeof(_lib.CnDist), _lib.CnDist.episode_base.offset, C.sizeof(_lib.PpoDist)]
     assert got == want
 
 
 def test_argument_validation_without_gpu(lib):
     from icrl_b200 import _lib
-    assert lib.icrl_abi_version() == 1
+    assert lib.icrl_abi_version() == _lib.ABI_VERSION == 2
     d = _lib.CnDesc()
     assert lib.icrl_cn_param_count(C.byref(d)) == -1                     # empty descriptor is rejected
     assert b"obs_dim" in lib.icrl_last_error()

@@ -21,11 +21,13 @@ def build(d, shape):
     if not s["is_discrete"]:
         low, high = -np.ones(s["acs_dim"], np.float32), np.ones(s["acs_dim"], np.float32)
     lr = float(d["lr"])
-    cn = ConstraintNet(s["obs_dim"], s["acs_dim"], s["hidden"], None, lambda x: lr, d["expert_obs"], d["expert_acs"],
+    batch_size = int(d["batch_size"]) if int(d.get("batch_size", 0)) > 0 else None
+    cn = ConstraintNet(s["obs_dim"], s["acs_dim"], s["hidden"], batch_size, lambda x: lr, d["expert_obs"], d["expert_acs"],
                        s["is_discrete"], float(d["reg"]), no_importance_sampling=bool(d["no_is"]),
                        per_step_importance_sampling=bool(d["per_step"]), clip_obs=20., initial_obs_mean=d.get("obs_mean"),
                        initial_obs_var=d.get("obs_var"), action_low=low, action_high=high,
-                       target_kl_old_new=float(d["tkon"]), target_kl_new_old=float(d["tkno"]))
+                       target_kl_old_new=float(d["tkon"]), target_kl_new_old=float(d["tkno"]),
+                       train_gail_lambda=bool(d.get("gail", False)))
     cn.load_network_state_dict({k[3:]: th.tensor(v) for k, v in d.items() if k.startswith("p0.")})
     return cn
 
@@ -38,10 +40,15 @@ def net_params(cn):
 def test_train_matches_reference(case):
     d = load_golden(f"k2_{case}")
     cn = build(d, case.split("_")[0])
+    if "numpy_seed" in d:                 # -cbs fixtures: the minibatch permutations come from the global numpy RNG
+        np.random.seed(int(d["numpy_seed"]))
     for call in (1, 2):
         if f"p{call}.0.weight" not in d:
             break
         m = cn.train(int(d["iters"]), d["nominal_obs"], d["nominal_acs"], d["lengths"], d.get("obs_mean"), d.get("obs_var"), 1.0)
+        if f"rng_pos{call}" in d:         # ... and is left where the reference leaves it (early stops included)
+            st = np.random.get_state()
+            assert st[2] == int(d[f"rng_pos{call}"]) and (st[1][:4].astype(np.int64) == d[f"rng_probe{call}"]).all()
         ref = [d[k] for k in sorted(k for k in d if k.startswith(f"p{call}."))]
         # sorted() orders 0.bias before 0.weight; state_dict order is weight, bias -> compare by key instead
         sd = cn.network.state_dict()

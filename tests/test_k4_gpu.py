@@ -86,6 +86,39 @@ def test_train_matches_reference(case):
     assert np.allclose(algo.dual.nu.log_nu.cpu().numpy(), d["log_nu2"], rtol=1e-5)
 
 
+K4X_CASES = sorted(os.path.basename(p)[4:-4] for p in glob.glob(os.path.join(GOLDEN, "k4x_*.npz")))
+# parameters vs the reference after every train() of the round-2 fixtures.  hc_full is the drift test: 1 600 DEPENDENT
+# optimiser steps (a whole HalfCheetah rollout: 2048 x 5, batch 64, 10 epochs) with 3xTF32 products, sqrt.approx and a fast
+# division in Adam; the bound is what a chain of that length allows, the measured figure is in DESIGN.md section 2.
+K4X_TOL = {"hc_full": 2e-3}
+
+
+@pytest.mark.parametrize("case", K4X_CASES)
+def test_full_size_and_large_batch_match_reference(case):
+    """Round-2 fixtures: the full-size launch and the large-batch regime (batch >= 2048 selects the many-cluster kernel;
+    ragged last minibatch, discrete actions, value clipping, full batch, KL early stop across launches)."""
+    from icrl_b200 import logger
+    from helpers import load_k4x
+    d = load_k4x(case)
+    algo, hp, names = build_algo(d)
+    logger.configure()
+    np.random.seed(int(hp["numpy_seed"]))
+    tol = K4X_TOL.get(case, PARAM_RTOL)
+    for call in range(1, int(hp["trains"]) + 1):
+        algo.train()
+        err = max_param_err(params_of(algo, names), [d[f"p{call}." + n] for n in names])
+        print(f"k4x {case}: train() #{call}: {algo.policy.optimizer.step_count} optimiser steps, max param err {err:.3e}")
+        assert err <= tol * (1 if call == 1 else 3), f"params after train() #{call}: {err}"
+        assert np.allclose(algo.dual.nu.log_nu.cpu().numpy(), d[f"log_nu{call}"], rtol=1e-5)
+        if call == 1:
+            log = {k[4:]: float(v) for k, v in d.items() if k.startswith("log.")}
+            got = logger.Logger.CURRENT.name_to_value
+            assert int(got["train/early_stop_epoch"]) == int(log["train/early_stop_epoch"])
+            for k in ("train/entropy_loss", "train/policy_gradient_loss", "train/reward_value_loss", "train/cost_value_loss",
+                      "train/clip_fraction", "train/loss", "train/approx_kl"):
+                assert abs(float(got[k]) - log[k]) <= 5e-4 * max(abs(log[k]), 1e-2), (k, float(got[k]), log[k])
+
+
 def test_one_update_and_adam_state():
     """The north-star gate: parameters after ONE optimiser step <= 1e-4, plus the Adam moments themselves."""
     d = load_golden("k4_hc_fullbatch")

@@ -58,14 +58,21 @@ def test_k2_train_matches_reference(case):
     shape = case.split("_")[0]
     spec = cn_spec(shape, d, regularizer_coeff=float(d["reg"]), importance_sampling=not bool(d["no_is"]),
                    per_step_importance_sampling=bool(d["per_step"]), target_kl_old_new=float(d["tkon"]),
-                   target_kl_new_old=float(d["tkno"]))
+                   target_kl_new_old=float(d["tkno"]), train_gail_lambda=bool(d.get("gail", False)))
     params = cn_params(d, "p0.")
     adam = ocn.adam_init(params)
+    batch_size = int(d["batch_size"]) if int(d.get("batch_size", 0)) > 0 else None    # -cbs minibatch fixtures (round 2)
+    if "numpy_seed" in d:
+        np.random.seed(int(d["numpy_seed"]))
     for call in (1, 2):
         if f"p{call}.0.weight" not in d:
             break
         m = ocn.train(params, adam, spec, int(d["iters"]), d["nominal_obs"], d["nominal_acs"], d["lengths"],
-                      d["expert_obs"], d["expert_acs"], lr=float(d["lr"]), materialize_broadcast=True)
+                      d["expert_obs"], d["expert_acs"], lr=float(d["lr"]), materialize_broadcast=True,
+                      batch_size=batch_size)
+        if f"rng_pos{call}" in d:       # the global numpy RNG stands where the reference left it
+            st = np.random.get_state()
+            assert st[2] == int(d[f"rng_pos{call}"]) and (st[1][:4].astype(np.int64) == d[f"rng_probe{call}"]).all()
         ref = cn_params(d, f"p{call}.")
         assert max_param_err([p.numpy() for p in params], [p.numpy() for p in ref]) <= 1e-6
         for k, v in m.items():
@@ -130,9 +137,18 @@ def k4_kwargs(hp, is_discrete, nu):
                 clip_range_cost_vf=opt("clip_range_cost_vf"))
 
 
-@pytest.mark.parametrize("case", K4_CASES)
+K4X_CASES = sorted(os.path.basename(p)[4:-4] for p in glob.glob(os.path.join(GOLDEN, "k4x_*.npz")))
+
+
+@pytest.mark.parametrize("case", K4_CASES + ["x:" + c for c in K4X_CASES])
 def test_k4_train_matches_reference(case):
-    d = load_golden(f"k4_{case}")
+    """k4_*: small fixtures; x:* (round 2): the full-size HalfCheetah train() (1 600 dependent optimiser steps) and the
+    large-batch regime (batch >= 2048), inputs regenerated from their seed."""
+    if case.startswith("x:"):
+        from helpers import load_k4x
+        d = load_k4x(case[2:])
+    else:
+        d = load_golden(f"k4_{case}")
     is_discrete = "log_std" not in [str(n) for n in d["param_order"]]
     flat, hp = k4_inputs(d)
     P = policy_params(d, "p0.")
@@ -140,7 +156,7 @@ def test_k4_train_matches_reference(case):
     dual = oppo.dual_init(hp["penalty_initial_value"])
     assert np.allclose(dual["log_nu"].numpy(), d["log_nu0"], rtol=0, atol=0)
     n = flat["observations"].shape[0]
-    for call in (1, 2):
+    for call in range(1, int(hp.get("trains", 2)) + 1):
         if call == 1:
             np.random.seed(int(hp["numpy_seed"]))
         nu = oppo.dual_nu(dual).item()
@@ -156,7 +172,9 @@ def test_k4_train_matches_reference(case):
         oppo.dual_step(dual, np.mean(d["buf.orig_costs"]), 0.0, hp["penalty_learning_rate"])
         ref = policy_params(d, f"p{call}.")
         err = max_param_err([p.numpy() for p in P.values()], [p.numpy() for p in ref.values()])
-        assert err <= 2e-5, err
+        # 1 600 dependent steps amplify last-bit differences between the oracle's explicit-weight autograd graph and the
+        # reference's modules (hc_full: measured 6e-5)
+        assert err <= (1e-4 if case == "x:hc_full" else 2e-5), err
         assert np.allclose(dual["log_nu"].numpy(), d[f"log_nu{call}"], rtol=1e-6)
         if call == 1:
             log = {k[4:]: float(v) for k, v in d.items() if k.startswith("log.")}
