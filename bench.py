@@ -9,8 +9,13 @@ One "step" = one full ICRL learner iteration on synthetic buffers of the named e
 `value`  : whole-job transitions/s with all inputs resident in HBM (icrl_b200.learner.DeviceLearner, C-ABI device entry points).
 `e2e`    : the same iteration through the reference-shaped Python API with HOST (numpy) buffers: ConstraintNet.cost_function,
            RolloutBufferWithCost.compute_returns_and_advantage, PPOLagrangian.train, ConstraintNet.train -- H2D / D2H inside.
-`roofline`: the dominant kernel (K4 persistent PPO kernel), algorithmic bytes / measured launch duration vs measured HBM peak.
-`cpu_baseline`: the oracle (CPU restatement of the reference, torch-CPU + numpy) on a bounded sample, extrapolated linearly.
+`roofline`: the dominant kernel (K4 persistent PPO kernel): algorithmic bytes AND flops / measured launch duration against the
+           measured HBM and 3xTF32 tensor peaks, the binding one named.
+`workloads`: short runs of the other BASELINE configs (AntWall, LapGrid, PointCircle; N>1: AntWall), same value / e2e / roofline.
+`sweep`   : the Ant-shaped 64K-16M transition sweep (BASELINE config 5), K1-K4 per size against their rooflines.
+`dp_parity`: N>1 only -- the data-parallel K4 / K2 paths checked against the oracle before anything is timed.
+`cpu_baseline`: the UNMODIFIED reference (baseline/_ref) on a bounded sample of the same iteration, extrapolated linearly
+           (the oracle port only if that copy is absent).
 Fixed work: KL early stops (ppo target_kl, cn target_kl_*) are disabled so every epoch / backward iteration runs.
 """
 import argparse
@@ -48,6 +53,10 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=1600, help="K4 optimiser steps in the CPU sample (one full HalfCheetah rollout)")
     ap.add_argument("--replicas", action="store_true", help="N>1: independent learners instead of data-parallel all-reduce")
     ap.add_argument("--ref-budget", type=float, default=150.0, help="--impl reference: seconds of CPU work for all samples")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the short AntWall / LapGrid / PointCircle runs")
+    ap.add_argument("--aux-steps", type=int, default=2, help="timed iterations of each secondary workload")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the Ant-shaped 64K-16M transition sweep")
+    ap.add_argument("--sweep-sizes", default="65536,262144,1048576,4194304,16777216", help="transitions per GPU")
     return ap.parse_args()
 
 
@@ -331,16 +340,19 @@ class _Env:
 class HostLearner:
     """The same iteration through ConstraintNet / RolloutBufferWithCost / PPOLagrangian with numpy buffers."""
 
-    def __init__(self, w, dev_learner):
+    def __init__(self, w, dev_learner, rank=0):
         from icrl_b200.buffers import RolloutBufferWithCost
         from icrl_b200.ppo_lag import PPOLagrangian
-        self.w, self.cn = w, dev_learner.cn
+        self.w, self.cn = w, dev_learner.cn        # (in data-parallel mode the constraint net is already sharded: cn.comm)
         E = dev_learner.E
         self.algo = PPOLagrangian("TwoCriticsMlpPolicy", _Env(w, E), n_steps=w.n_steps, batch_size=w.batch_size,
                                   n_epochs=w.n_epochs, learning_rate=w.learning_rate, clip_range=w.clip_range,
                                   reward_gae_lambda=w.reward_gae_lambda, cost_gae_lambda=w.cost_gae_lambda, target_kl=None,
                                   penalty_initial_value=w.penalty_initial_value, penalty_learning_rate=w.penalty_learning_rate,
                                   seed=0, device=dev_learner.dev)
+        if dev_learner.comm is not None and dev_learner.comm.world > 1:
+            self.algo.policy.load_state_dict(dev_learner.policy.state_dict())      # replicated start on every rank
+            self.algo.enable_data_parallel(dev_learner.comm)
         host = dev_learner.host
         self.bufs, self.pristine = [], []
         for r in range(w.rollouts):
@@ -366,7 +378,7 @@ class HostLearner:
                                         norm_cost=True, training=True, old_cost=None)
         if w.nominal_rows:
             from icrl_b200.learner import synth_demos
-            _, _, self.no, self.na, self.lengths = synth_demos(w, 0)
+            _, _, self.no, self.na, self.lengths = synth_demos(w, rank)
         self.h2d = self.d2h = 0
 
     def run(self):
@@ -410,16 +422,29 @@ def time_steps(fn, steps, world, flush):
     return max_over_ranks(sum(s.elapsed_time(e) for s, e in evs) * 1e-3, world)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE full K4 launch, from the `ncu --set full` captures summarised in
-# profiles/SUMMARY_r01.md (gpurun_out/k4_r01.ncu-rep, k4_ant_r01.ncu-rep); keyed by Workload.name
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE full single-cluster K4 launch: an OFFLINE constant from the
+# `ncu --set full` captures summarised under profiles/ (not measured in this run: ncu replays kernels and bench numbers may not
+# be taken under a profiler); keyed by Workload.name
 K4_NCU_TRAFFIC_BYTES = {
     "HalfCheetah HCWithPos-v0 ICRL (cl 20, ft 2e5, bi 10)": 21652480,
     "AntWall-v0 ICRL (cl 40 40, ft 2e5, bi 5, batch 128, n_epochs 20)": 122238720 + 3342848,
 }
 
 
-def kernel_roofline(learner, peak, peak_src):
-    """Dominant kernel = the persistent K4 launch: CUDA events around each of R launches on the launching stream."""
+def k4_flops_per_sample_pass(w):
+    """2 * MACs of the three trunks + heads, forward + backward ~ 3x forward."""
+    a_out = w.act_dim
+    fwd = 2 * (3 * (w.obs_dim * 64 + 64 * 64) + 64 * (a_out + 2))
+    return 3 * fwd
+
+
+def k4_bytes_per_sample_pass(w):
+    return (w.obs_dim + (1 if w.is_discrete else w.act_dim) + 7) * 4
+
+
+def kernel_roofline(learner, peaks):
+    """Dominant kernel = the persistent K4 launch: CUDA events around each of R launches on the launching stream.
+    Both rooflines are evaluated; `bound` names the binding one (the lower attainable throughput), as SURVEY 8(d) asks."""
     import ctypes as C
     from icrl_b200 import _lib
     w = learner.w
@@ -444,67 +469,283 @@ def kernel_roofline(learner, peak, peak_src):
         times.append(s.elapsed_time(e) * 1e-3)
     dur = float(np.mean(times))
     steps = w.n_epochs * learner.steps_per_epoch
-    bytes_per_pass = (w.obs_dim + (1 if w.is_discrete else w.act_dim) + 7) * 4
-    alg_bytes = bytes_per_pass * learner.n * w.n_epochs
-    achieved = alg_bytes / dur / 1e9
-    return {"bound": "hbm", "kernel": "ppo_train_kernel (K4, persistent 6-CTA cluster: a CTA pair per trunk)",
-            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": K4_NCU_TRAFFIC_BYTES.get(learner.w.name), "peak_source": peak_src,
-            "launch_ms": dur * 1e3, "optimiser_steps_per_launch": steps, "us_per_optimiser_step": dur / steps * 1e6,
-            "algorithmic_bytes_per_launch": alg_bytes,
-            "note": "1600 dependent optimiser steps on 64-128 rows each: latency-bound by construction (SURVEY §7), "
-                    "so the HBM fraction is tiny; us_per_optimiser_step is the figure of merit.  ncu on the same launch "
-                    "(profiles/SUMMARY_r01.md): tensor pipe active 20.6 %, 8 of 64 warp slots, the GEMM phases run at ~2x their "
-                    "mma.sync issue bound"}
+    passes = learner.n * w.n_epochs
+    alg_bytes = k4_bytes_per_sample_pass(w) * passes
+    alg_flops = k4_flops_per_sample_pass(w) * passes
+    gbs, tfs = alg_bytes / dur / 1e9, alg_flops / dur / 1e12
+    tc_peak = peaks["tf32_mma_tflops"] / 3.0          # one fp32-class product = three TF32 MMAs (hi*hi + hi*lo + lo*hi)
+    t_hbm, t_tc = alg_bytes / (peaks["hbm_gbs"] * 1e9), alg_flops / (tc_peak * 1e12)
+    binding = "tensor" if t_tc >= t_hbm else "hbm"
+    out = {"bound": binding, "kernel": "ppo_train_kernel (K4, persistent 6-CTA cluster: a CTA pair per trunk)",
+           "achieved": tfs if binding == "tensor" else gbs, "peak": tc_peak if binding == "tensor" else peaks["hbm_gbs"],
+           "unit": "TFLOP/s" if binding == "tensor" else "GB/s",
+           "frac": (tfs / tc_peak) if binding == "tensor" else gbs / peaks["hbm_gbs"],
+           "traffic": K4_NCU_TRAFFIC_BYTES.get(learner.w.name),
+           "traffic_source": "offline constant: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full "
+                             "capture summarised under profiles/ (not measured in this run)",
+           "peak_source": peaks["source"],
+           "hbm": {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"]},
+           "tensor": {"achieved": tfs, "peak": tc_peak, "unit": "TFLOP/s", "frac": tfs / tc_peak,
+                      "what": "fp32-class 3xTF32 products on mma.sync.m16n8k8: measured TF32 mma.sync rate / 3",
+                      "frac_of_fp32_ffma_peak": tfs / peaks["fp32_tflops"],
+                      "frac_of_bf16_cublas_peak": tfs / peaks["bf16_tflops"] if peaks.get("bf16_tflops") else None},
+           "launch_ms": dur * 1e3, "optimiser_steps_per_launch": steps, "us_per_optimiser_step": dur / steps * 1e6,
+           "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_flops_per_launch": alg_flops,
+           "note": f"{steps} DEPENDENT optimiser steps on {w.batch_size} rows each: neither roofline is approachable at the "
+                   "reference's batch size (SURVEY 7: step latency); us_per_optimiser_step is the figure of merit here and the "
+                   "batch-scaled sweep (`sweep`) is where the kernels are held against their rooflines"}
+    return out
 
 
-def family_rooflines(learner, peak):
-    """Per-family achieved HBM GB/s for the streaming kernels (K1 relabel, K3 GAE) at the workload's rollout size and at a
-    4M-transition sweep point (inputs > L2)."""
+def family_rooflines(learner, peaks):
+    """Per-family achieved HBM GB/s for the streaming kernels (K1 relabel, K3 GAE, K5) at the workload's rollout size."""
     import ctypes as C
     from icrl_b200 import _lib
     w, L = learner.w, _lib.lib()
+    peak = peaks["hbm_gbs"]
     out = {}
-
-    def timeit(fn, reps=5):
-        fn(); th.cuda.synchronize()
-        ts = []
-        for _ in range(reps):
-            s, e = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
-            s.record(); fn(); e.record(); th.cuda.synchronize()
-            ts.append(s.elapsed_time(e) * 1e-3)
-        return float(np.median(ts))
 
     desc = learner.cn._get_desc()
     k1_bytes_row = (learner.cn.input_dims + 1) * 4
-    for tag, T, E in (("rollout", w.n_steps, learner.E), ("sweep_4M", 2048, 2048)):
-        n = T * E
-        obs = th.randn(n, w.obs_dim, device=learner.dev)
-        acs = (th.randint(0, w.act_dim, (n,), device=learner.dev).float() if w.is_discrete
-               else th.randn(n, w.act_dim, device=learner.dev))
-        cost = th.empty(n, device=learner.dev)
-        d = timeit(lambda: _lib.check(L.icrl_cn_forward(C.byref(desc), _lib.ptr(obs), 0, _lib.ptr(acs), n, _lib.ptr(cost), 0,
+    T, E = w.n_steps, learner.E
+    n = T * E
+    obs = th.randn(n, w.obs_dim, device=learner.dev)
+    acs = (th.randint(0, w.act_dim, (n,), device=learner.dev).float() if w.is_discrete
+           else th.randn(n, w.act_dim, device=learner.dev))
+    cost = th.empty(n, device=learner.dev)
+    d = timeit(lambda: _lib.check(L.icrl_cn_forward(C.byref(desc), _lib.ptr(obs), 0, _lib.ptr(acs), n, _lib.ptr(cost), 0,
+                                                    _lib.current_stream())))
+    out["k1_rollout"] = {"rows": n, "us": d * 1e6, "GB/s": k1_bytes_row * n / d / 1e9, "frac_hbm": k1_bytes_row * n / d / 1e9 / peak}
+    arrs = [th.randn(T, E, device=learner.dev) for _ in range(4)] + [(th.rand(T, E, device=learner.dev) < 0.002).float()]
+    lv = [th.randn(E, device=learner.dev) for _ in range(2)] + [th.zeros(E, dtype=th.uint8, device=learner.dev)]
+    outs = [th.empty(T, E, device=learner.dev) for _ in range(4)]
+    d = timeit(lambda: _lib.check(L.icrl_dual_gae(*[_lib.ptr(x) for x in arrs + lv], T, E, 0.99, 0.95, 0.99, 0.95,
+                                                  *[_lib.ptr(o) for o in outs], _lib.current_stream())))
+    out["k3_rollout"] = {"rows": n, "us": d * 1e6, "GB/s": 36 * n / d / 1e9, "frac_hbm": 36 * n / d / 1e9 / peak}
+    # K5: T-serial float64 statistics chain (bit-exact with numpy) -- latency-bound, not a bandwidth kernel
+    state = th.tensor([0.0, 1.0, 1e-4] + [0.0] * E, dtype=th.float64, device=learner.dev)
+    d = timeit(lambda: _lib.check(L.icrl_cost_normalize(_lib.ptr(arrs[0]), _lib.ptr(arrs[4]), _lib.ptr(lv[2]), T, E,
+                                                        0.99, 1e-8, 10.0, 1, 1, _lib.ptr(state), _lib.ptr(outs[0]),
                                                         _lib.current_stream())))
-        out[f"k1_{tag}"] = {"rows": n, "us": d * 1e6, "GB/s": k1_bytes_row * n / d / 1e9, "frac_hbm": k1_bytes_row * n / d / 1e9 / peak}
-        arrs = [th.randn(T, E, device=learner.dev) for _ in range(4)] + [(th.rand(T, E, device=learner.dev) < 0.002).float()]
-        lv = [th.randn(E, device=learner.dev) for _ in range(2)] + [th.zeros(E, dtype=th.uint8, device=learner.dev)]
-        outs = [th.empty(T, E, device=learner.dev) for _ in range(4)]
-        d = timeit(lambda: _lib.check(L.icrl_dual_gae(*[_lib.ptr(x) for x in arrs + lv], T, E, 0.99, 0.95, 0.99, 0.95,
-                                                      *[_lib.ptr(o) for o in outs], _lib.current_stream())))
-        out[f"k3_{tag}"] = {"rows": n, "us": d * 1e6, "GB/s": 36 * n / d / 1e9, "frac_hbm": 36 * n / d / 1e9 / peak}
-        if tag == "rollout":
-            # K5: T-serial float64 statistics chain (bit-exact with numpy) -- latency-bound, not a bandwidth kernel
-            state = th.tensor([0.0, 1.0, 1e-4] + [0.0] * E, dtype=th.float64, device=learner.dev)
-            d = timeit(lambda: _lib.check(L.icrl_cost_normalize(_lib.ptr(arrs[0]), _lib.ptr(arrs[4]), _lib.ptr(lv[2]), T, E,
-                                                                0.99, 1e-8, 10.0, 1, 1, _lib.ptr(state), _lib.ptr(outs[0]),
-                                                                _lib.current_stream())))
-            out["k5_rollout"] = {"rows": n, "us": d * 1e6, "GB/s": 13 * n / d / 1e9, "frac_hbm": 13 * n / d / 1e9 / peak}
+    out["k5_rollout"] = {"rows": n, "us": d * 1e6, "GB/s": 13 * n / d / 1e9, "frac_hbm": 13 * n / d / 1e9 / peak}
     return out
+
+
+def timeit(fn, reps=5):
+    fn(); th.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        s, e = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record(); th.cuda.synchronize()
+        ts.append(s.elapsed_time(e) * 1e-3)
+    return float(np.median(ts))
+
+
+def ant_sweep(rank, world, dev, ppo_comm, peaks, sizes):
+    """BASELINE config 5: synthetic Ant-shaped buffers of N transitions PER GPU (weak scaling), N in `sizes`; every kernel
+    family on device-resident data, max over ranks.  K1 rows, K3 env columns shard with no collective; K2 (sharded by episodes,
+    2 backward iterations, per-step IS) and K4 (batch = N/80 rows per rank -> the many-cluster kernel, 2 epochs = 160 optimiser
+    steps, gradients all-reduced inside the kernel) exchange over NVLink peer memory.  Each entry carries achieved GB/s and
+    TFLOP/s against the measured HBM, FP32-FFMA and 3xTF32 peaks and names the binding roofline."""
+    import ctypes as C
+    from icrl_b200 import _lib
+    from icrl_b200.constraint_net import ConstraintNet
+    from icrl_b200.learner import WORKLOADS, spaces_of
+    from icrl_b200.policies import ActorTwoCriticsPolicy
+    L = _lib.lib()
+    w = WORKLOADS["antwall"]
+    D, A = w.obs_dim, w.act_dim
+    hbm, fp32, tc = peaks["hbm_gbs"], peaks["fp32_tflops"], peaks["tf32_mma_tflops"] / 3.0
+    th.manual_seed(0)
+    low, high = -np.ones(A, np.float32), np.ones(A, np.float32)
+    obs_space, act_space = spaces_of(w)
+    rows_out = []
+
+    def entry(rows, dur, bytes_per, flops_per, compute_peak, compute_name):
+        dur = max_over_ranks(dur, world)
+        gbs, tfs = bytes_per * rows / dur / 1e9, flops_per * rows / dur / 1e12
+        f_h, f_c = gbs / hbm, tfs / compute_peak
+        t_h, t_c = bytes_per / (hbm * 1e9), flops_per / (compute_peak * 1e12)
+        return {"rows_per_gpu": rows, "ms": dur * 1e3, "rows_per_s_all_gpus": rows * world / dur, "GB/s_per_gpu": gbs,
+                "frac_hbm": f_h, "TFLOP/s_per_gpu": tfs, f"frac_{compute_name}": f_c, "bound": "hbm" if t_h >= t_c else compute_name,
+                "frac_of_binding_roofline": f_h if t_h >= t_c else f_c}
+
+    for N in sizes:
+        T = 2048
+        E = N // T
+        n = T * E
+        ent = {"transitions_per_gpu": n}
+        obs = th.randn(n, D, device=dev) * 3.0
+        acs = th.randn(n, A, device=dev)
+        # ---- K1
+        cn = ConstraintNet(D, A, w.cn_hidden, None, lambda _: w.cn_lr, obs[:8].cpu().numpy(), acs[:8].cpu().numpy(), False,
+                           w.cn_reg, per_step_importance_sampling=True, clip_obs=20., action_low=low, action_high=high,
+                           target_kl_old_new=-1, target_kl_new_old=-1, device=dev)
+        desc = cn._get_desc()
+        cost = th.empty(n, device=dev)
+        barrier(world)
+        d = timeit(lambda: _lib.check(L.icrl_cn_forward(C.byref(desc), _lib.ptr(obs), 0, _lib.ptr(acs), n, _lib.ptr(cost), 0,
+                                                        _lib.current_stream())), reps=3)
+        ent["k1"] = entry(n, d, (cn.input_dims + 1) * 4, 2 * (121 * 40 + 40 * 40 + 40), fp32, "fp32")
+        # ---- K3
+        arrs = [th.randn(T, E, device=dev) for _ in range(4)] + [(th.rand(T, E, device=dev) < 0.002).float()]
+        lv = [th.randn(E, device=dev) for _ in range(2)] + [th.zeros(E, dtype=th.uint8, device=dev)]
+        outs = [th.empty(T, E, device=dev) for _ in range(4)]
+        barrier(world)
+        d = timeit(lambda: _lib.check(L.icrl_dual_gae(*[_lib.ptr(x) for x in arrs + lv], T, E, 0.99, 0.9, 0.99, 0.9,
+                                                      *[_lib.ptr(o) for o in outs], _lib.current_stream())), reps=3)
+        ent["k3"] = entry(n, d, 36, 14, fp32, "fp32")
+        # ---- K2: nominal n rows in 500-step episodes, expert n rows, 2 backward iterations
+        iters = 2
+        n_ep = n // 500
+        off = th.arange(0, n_ep + 1, dtype=th.int32, device=dev) * 500
+        n2 = n_ep * 500
+        cfg2 = _lib.CnTrainCfg(iterations=iters, importance_sampling=1, per_step_is=1, train_gail_lambda=0, eps=1e-5,
+                               regularizer_coeff=float(w.cn_reg), target_kl_old_new=-1.0, target_kl_new_old=-1.0,
+                               lr=float(w.cn_lr), adam_beta1=0.9, adam_beta2=0.999, adam_eps=1e-5, batch_size=0, perm=None)
+        metrics = _lib.CnTrainMetrics()
+        dp = world > 1 and ppo_comm is not None
+        if dp:
+            cn.enable_data_parallel(max_episodes=2 * n_ep * world)
+
+        def k2():
+            step = C.c_int64(cn.optimizer.step_count)
+            args = (C.byref(desc), C.byref(cfg2), _lib.ptr(obs), 0, _lib.ptr(acs), n2, _lib.ptr(off), n_ep, _lib.ptr(obs), 0,
+                    _lib.ptr(acs), n, _lib.ptr(cn._adam_m), _lib.ptr(cn._adam_v), C.byref(step), C.byref(metrics))
+            if dp:
+                dd = cn.comm.descriptor(n2 * world, n * world, n_ep * world, n_ep * rank)
+                _lib.check(L.icrl_cn_train_dist(*args, C.byref(dd), _lib.current_stream()))
+                cn.comm.advance(iters)
+            else:
+                _lib.check(L.icrl_cn_train(*args, _lib.current_stream()))
+        barrier(world)
+        d = timeit(k2, reps=2)
+        # per backward iteration: IS forward over the nominal rows + forward/backward over nominal and expert rows
+        cn_fwd = 2 * (121 * 40 + 40 * 40 + 40)
+        ent["k2"] = entry(n2 * iters, d, 121 * 4 * 3 + 12, cn_fwd + 3 * cn_fwd * 2, fp32, "fp32")
+        ent["k2"]["backward_iterations"] = iters
+        if dp:
+            cn.comm.close()
+        # ---- K4: batch = n / 80 rows per rank (80 optimiser steps per epoch like the reference's 10 240 / 128), 2 epochs
+        n_epochs, B = 2, max(2048, n // 80)
+        pol = ActorTwoCriticsPolicy(obs_space, act_space, lambda _: w.learning_rate, device=dev)
+        spe = -(-n // B)
+        cfg4 = pol.make_cfg(T=T, E=E, batch_size=B, n_epochs=n_epochs, has_target_kl=0, target_kl=0.0, clip_range=w.clip_range,
+                            ent_coef=0.0, reward_vf_coef=0.5, cost_vf_coef=0.5, max_grad_norm=0.5, nu=0.1, max_steps=0)
+        sc = [th.randn(T, E, device=dev) for _ in range(6)]
+        logp = th.randn(T, E, device=dev) * 0.1 - 11.3
+        perm = th.stack([th.randperm(n, device=dev) for _ in range(n_epochs)]).to(th.int32)
+        data = _lib.PpoData()
+        data.observations, data.actions, data.old_log_prob = obs.data_ptr(), acs.data_ptr(), logp.data_ptr()
+        data.old_reward_values, data.reward_advantages, data.reward_returns = (x.data_ptr() for x in sc[:3])
+        data.old_cost_values, data.cost_advantages, data.cost_returns = (x.data_ptr() for x in sc[3:])
+        data.perm = perm.data_ptr()
+        stats = th.zeros(n_epochs * spe, 8, device=dev)
+        result = th.zeros(4, dtype=th.int32, device=dev)
+        advsums = th.zeros(n_epochs * spe, 4, dtype=th.float64, device=dev)
+
+        def k4():
+            if dp:
+                _lib.check(L.icrl_ppo_local_advsums(C.byref(cfg4), C.byref(data), _lib.ptr(advsums), _lib.current_stream()))
+                ppo_comm.all_reduce_sum(advsums)
+                dd = ppo_comm.descriptor(advsums)
+                _lib.check(L.icrl_ppo_train_dist(C.byref(cfg4), C.byref(data), _lib.ptr(pol._params), _lib.ptr(pol._adam_m),
+                                                 _lib.ptr(pol._adam_v), pol.optimizer.step_count, _lib.ptr(stats),
+                                                 _lib.ptr(result), C.byref(dd), _lib.current_stream()))
+                ppo_comm.advance(n_epochs * spe)
+            else:
+                _lib.check(L.icrl_ppo_train(C.byref(cfg4), C.byref(data), _lib.ptr(pol._params), _lib.ptr(pol._adam_m),
+                                            _lib.ptr(pol._adam_v), pol.optimizer.step_count, _lib.ptr(stats), _lib.ptr(result),
+                                            _lib.current_stream()))
+            pol.optimizer.step_count += n_epochs * spe
+        barrier(world)
+        d = timeit(k4, reps=2)
+        res = result.cpu().numpy()
+        ent["k4"] = entry(n * n_epochs, d, k4_bytes_per_sample_pass(w), k4_flops_per_sample_pass(w), tc, "tensor_3xtf32")
+        ent["k4"].update(batch_size_per_gpu=B, global_batch=B * (world if dp else 1), optimiser_steps=int(res[1]), peer_timeout=bool(res[2]),
+                         us_per_optimiser_step=max_over_ranks(d, world) / max(int(res[1]), 1) * 1e6)
+        rows_out.append(ent)
+        del obs, acs, cost, arrs, outs, sc, logp, perm, stats, advsums, pol, cn
+        th.cuda.empty_cache()
+    return rows_out
+
+
+def run_workload(name, args, rank, world, local, ppo_comm, peaks, flush, steps, warmup, want_e2e, want_family):
+    """value (device-resident DeviceLearner), e2e (host-buffer public API) and the K4 launch roofline of one named workload."""
+    from icrl_b200 import _lib
+    from icrl_b200.learner import WORKLOADS, DeviceLearner
+    w = WORKLOADS[name]
+    dev = th.device("cuda", local)
+    # data parallel: every rank owns n_envs environments (its own rollouts, seed = rank); networks replicated
+    learner = DeviceLearner(w, seed=rank, device=dev, comm=ppo_comm, param_seed=0)
+    for _ in range(warmup):
+        learner.run()
+    th.cuda.synchronize()
+    learner.check()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.lib().icrl_launch_count()
+    t_dev = time_steps(learner.run, steps, world, flush)
+    launches = _lib.lib().icrl_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    learner.check()                                   # raises on an exchange time-out (result[2]) in any K4 launch
+    per_step = t_dev / steps
+    total_tr = w.transitions_per_iteration * world
+    out = {"workload": w.name, "value": total_tr / per_step, "unit": UNIT, "ms_per_step": per_step * 1e3, "steps": steps,
+           "warmup": warmup, "gpu_launches": int(launches), "clocks": clocks}
+    dp = world > 1 and ppo_comm is not None
+    par = "1 GPU" if world == 1 else (
+        f"{world} independent learner replicas" if not dp else
+        f"dp{world}: env-sharded rollouts (K1/K5/K3 local), K4 gradients all-reduced inside the persistent kernel over NVLink "
+        f"peer memory every optimiser step (global batch {w.batch_size * world}), K2 sharded by episodes with in-kernel "
+        f"exchanges")
+    out["parallelism"] = par
+    if want_e2e:
+        hl = HostLearner(w, learner, rank)
+        for _ in range(2):
+            hl.run()
+        th.cuda.synchronize()
+        barrier(world)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            hl.run()
+        th.cuda.synchronize()
+        t_e2e = max_over_ranks(time.perf_counter() - t0, world) / steps
+        out["e2e"] = {"value": total_tr / t_e2e, "unit": UNIT,
+                      "parallelism": "1 GPU" if world == 1 else (f"dp{world} through PPOLagrangian.train / ConstraintNet.train "
+                                                                 "(enable_data_parallel)" if dp else f"{world} independent replicas"),
+                      "h2d_bytes_per_step": int(hl.h2d), "d2h_bytes_per_step": int(hl.d2h), "ms_per_step": t_e2e * 1e3,
+                      "path": "RolloutBufferWithCost.relabel_costs (or ConstraintNet.cost_function) / compute_returns_and_advantage"
+                              " / PPOLagrangian.train / ConstraintNet.train with numpy buffers (pinned staging + async H2D, "
+                              "D2H of costs, advantages, per-step stats, metrics)"}
+    if rank == 0:
+        out["roofline"] = kernel_roofline(learner, peaks)
+        if want_family:
+            out["kernels"] = family_rooflines(learner, peaks)
+    return out, learner
+
+
+def all_peaks():
+    """HBM (and bf16) from the driver-written MEASURED_PEAKS.json, FP32-FFMA and TF32 mma.sync measured here."""
+    import ctypes as C
+    from icrl_b200 import _lib
+    hbm, src = measured_peaks()
+    bf16 = None
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            bf16 = json.load(f).get("bf16_tflops")
+    two = (C.c_double * 2)()
+    _lib.check(_lib.lib().icrl_measure_peaks(two, _lib.current_stream()))
+    return {"hbm_gbs": hbm, "bf16_tflops": bf16, "fp32_tflops": float(two[0]), "tf32_mma_tflops": float(two[1]),
+            "source": f"HBM: {src}; FP32 FFMA {two[0]:.1f} TFLOP/s and mma.sync TF32 {two[1]:.1f} TFLOP/s measured in this run "
+                      "(icrl_measure_peaks: the instructions the kernels issue, every SM busy)"}
 
 
 def main():
     args = parse()
-    from icrl_b200.learner import WORKLOADS, DeviceLearner
+    from icrl_b200.learner import WORKLOADS
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, w)
@@ -512,72 +753,61 @@ def main():
     rank, world, local = dist_setup(args.gpus)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
     th.cuda.set_device(local)
-    from icrl_b200 import _lib
-    peak, peak_src = measured_peaks()
-    comm = None
+    dev = th.device("cuda", local)
+    peaks = all_peaks()
+    ppo_comm, dp_parity = None, None
     if world > 1 and not args.replicas:
         from icrl_b200.distributed import PpoComm
-        comm = PpoComm()
-    # data parallel: every rank owns n_envs environments (its own rollouts, seed = rank); networks and K2 batches replicated
-    learner = DeviceLearner(w, seed=rank, device=th.device("cuda", local), comm=comm, param_seed=0)
+        ppo_comm = PpoComm()
+        # data-parallel parity before anything is timed: rank-0 oracle check + bit-identical replicas across ranks
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import dp_worker
+        dp_parity = [dp_worker.ppo_parity(rank, world, dev, "hc", comm=ppo_comm),
+                     dp_worker.ppo_parity(rank, world, dev, "ant", comm=ppo_comm),
+                     dp_worker.ppo_parity(rank, world, dev, "ant", wide=True, comm=ppo_comm),
+                     dp_worker.cn_parity(rank, world, dev, "hc", per_step=True),
+                     dp_worker.cn_parity(rank, world, dev, "ant", per_step=False)]
+        if not all(p["ok"] for p in dp_parity):
+            raise SystemExit(f"data-parallel parity FAILED, nothing timed: {dp_parity}")
     flush = th.zeros(64 * 1024 * 1024, device="cuda")      # 256 MB
-    for _ in range(args.warmup):
-        learner.run()
-    th.cuda.synchronize()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    launches0 = _lib.lib().icrl_launch_count()
-    t_dev = time_steps(learner.run, args.steps, world, flush)
-    launches = _lib.lib().icrl_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    per_step = t_dev / args.steps
-    total_tr = w.transitions_per_iteration * world
-    value = total_tr / per_step
-
-    e2e = None
-    if not args.no_e2e:
-        hl = HostLearner(w, learner)
-        for _ in range(2):
-            hl.run()
-        th.cuda.synchronize()
-        barrier(world)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            hl.run()
-        th.cuda.synchronize()
-        t_e2e = max_over_ranks(time.perf_counter() - t0, world) / args.steps
-        e2e = {"value": total_tr / t_e2e, "unit": UNIT, "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas", "h2d_bytes_per_step": int(hl.h2d), "d2h_bytes_per_step": int(hl.d2h),
-               "ms_per_step": t_e2e * 1e3, "path": "ConstraintNet.cost_function / RolloutBufferWithCost.compute_returns_and_advantage"
-               " / PPOLagrangian.train / ConstraintNet.train with numpy buffers (pinned staging + async H2D, D2H of costs, "
-               "advantages, per-step stats, metrics)"}
-
-    roof = fam = cpu = None
-    if rank == 0:
-        roof = kernel_roofline(learner, peak, peak_src)
-        fam = family_rooflines(learner, peak)
+    main_out, learner = run_workload(args.workload, args, rank, world, local, ppo_comm, peaks, flush, args.steps, args.warmup,
+                                     not args.no_e2e, True)
+    del learner
+    th.cuda.empty_cache()
+    # the other BASELINE configs, short runs (N>1: AntWall only -- BASELINE config 3 is "AntWall on 1/2/4/8 B200")
+    others = {}
+    if not args.no_workloads:
+        names = [n for n in (("antwall", "lapgrid", "pointcircle") if world == 1 else ("antwall",)) if n != args.workload]
+        for n in names:
+            o, lrn = run_workload(n, args, rank, world, local, ppo_comm, peaks, flush, args.aux_steps, 3, not args.no_e2e, False)
+            others[n] = o
+            del lrn
+            th.cuda.empty_cache()
+    sweep = None
+    if not args.no_sweep:
+        sizes = [int(x) for x in args.sweep_sizes.split(",")]
+        sweep = ant_sweep(rank, world, dev, ppo_comm, peaks, sizes)
+    cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = pick_cpu_threads(w)
-        est, parts, sample = cpu_iteration_estimate(w, args.cpu_steps)
-        cpu = {"value": w.transitions_per_iteration / est, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-               "seconds_per_iteration_est": round(est, 2), "seconds_per_part": {k: round(v, 4) for k, v in parts.items()}}
+        from baseline import reference_arm as ra
+        if ra.available():
+            cpu = reference_samples(w, 1, 2, budget_s=24.0)
+        else:
+            cpu = port_samples(w, args, 1, 1)
     barrier(world)
     if rank == 0:
         print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": w.name, "transitions_per_step_per_gpu": w.transitions_per_iteration,
-                       "rollouts": w.rollouts, "n_steps": w.n_steps, "n_envs_per_gpu": w.n_envs, "batch_size": w.batch_size,
-                       "n_epochs": w.n_epochs, "backward_iters": w.backward_iters, "early_stop": "disabled (fixed work)",
-                       "l2": "flushed between timed steps (256 MB write, outside the timed region)",
-                       "parallelism": "1 GPU" if world == 1 else (
-                           f"{world} independent learner replicas" if args.replicas else
-                           f"dp{world}: env-sharded rollouts (K1/K3 local), K4 gradients all-reduced inside the persistent kernel "
-                           f"over NVLink peer memory every optimiser step (global batch {w.batch_size * world}), K2 replicated")},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "kernels": fam, "cpu_baseline": cpu}))
-    if comm is not None:
-        comm.close()
+            "metric": METRIC, "value": main_out["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main_out["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(w, world, main_out["parallelism"]),
+            "clocks": main_out["clocks"], "e2e": main_out.get("e2e"), "gpu_launches": main_out["gpu_launches"],
+            "roofline": main_out.get("roofline"), "kernels": main_out.get("kernels"), "peaks": peaks,
+            "dp_parity": None if dp_parity is None else {"ok": True, "checks": dp_parity,
+                                                          "max_param_err": max(p["max_param_err"] for p in dp_parity)},
+            "workloads": others, "sweep": sweep, "cpu_baseline": cpu}))
+    if ppo_comm is not None:
+        ppo_comm.close()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

@@ -74,7 +74,7 @@ class PpoDist(C.Structure):
                 ("flag_base", C.c_uint32), ("advsums", c_void)]
 
 
-PPO_RECV_BYTES = 2 * 8 * 6 * 72 * 256 * 8
+PPO_RECV_BYTES = 32 * 1024 * 1024
 PPO_FLAG_BYTES = 2 * 8 * 4 * 4
 
 # name -> (restype, argtypes); every symbol include/icrl_b200.h declares (checked by tests/test_abi.py)
@@ -83,6 +83,7 @@ SIGNATURES = {
     "icrl_last_error": (C.c_char_p, []),
     "icrl_launch_count": (C.c_int64, []),
     "icrl_device_info": (C.c_int, [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "icrl_measure_peaks": (C.c_int, [C.POINTER(C.c_double), c_void]),
     "icrl_cn_param_count": (C.c_int64, [C.POINTER(CnDesc)]),
     "icrl_cn_forward": (C.c_int, [C.POINTER(CnDesc), c_void, C.c_int32, c_void, C.c_int64, c_void, C.c_int32, c_void]),
     "icrl_cn_forward_host": (C.c_int, [C.POINTER(CnDesc), c_void, C.c_int32, c_void, C.c_int64, c_void, C.c_int32,

@@ -52,7 +52,15 @@ struct PpoArgs {
     int dist_mode;                // 0 auto (tagged broadcast + sum for 2 / 4 ranks, RS/AG for 8, {value, seq} words otherwise),
                                   // 1 {value, seq} words, 2 RS/AG, 3 broadcast + sum   (ICRL_PPO_DIST_MODE)
     const double* advsums;        // all-reduced per-step sums (sum adv_r, sum adv_r^2, sum adv_c, count) or NULL
+    // large-batch ("wide") mode: `ncl` 6-CTA clusters share every minibatch (one launch per epoch), see k4_ppo_lag.cu
+    int ncl, epoch_base, n_epochs_total;
+    float* wide_part;             // [3 trunks][ncl][F][256 threads]: every cluster's pair-summed gradient fragments
+    float* wide_red;              // [3 trunks][F][256 threads]: the cluster-order sums
+    unsigned int* wide_sync;      // [3 trunks] arrival counters of the grid-wide barriers (zeroed before every launch)
 };
+constexpr int WIDE_SMAX = 6;      // floats a (cluster, half) reducer sums per step: F <= 2 * ncl * WIDE_SMAX
+constexpr int WIDE_MAXCTA = 192;  // CTAs of a wide launch (<= 32 clusters) addressable in the data-parallel receive buffer
+constexpr int WIDE_MIN_BATCH = 2048;   // batch_size from which the many-cluster kernel is used
 constexpr int DIST_SLOTS = 72;    // floats per thread in a receive-buffer slab
 constexpr int RSAG_MAXW = 20;     // 16-byte words per (rank, role, thread) slab of the reduce-scatter / all-gather exchange:
                                   // layout [region 3][parity 2][src 8][role 3][RSAG_MAXW][256 threads] uint4 = 11.8 MB (regions: reduce-scatter, all-gather,

@@ -285,10 +285,22 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
 
 // ---------------------------------------------------------------- the persistent train kernel
 // NT1 = n-tiles of dW1 (64 x KP) each warp owns (warp w: m-tile w & 3, n-tiles (w >> 2) + 2 i).
-template <int NT1, bool DIST>
+// WIDE (large batches): the launch holds a.ncl such clusters and covers ONE epoch.  Every cluster keeps a full replica of the
+// weights / Adam moments and takes a contiguous slice of every minibatch; per optimiser step the clusters' pair-summed
+// gradients meet in global memory (L2): write -> grid barrier -> each (cluster, half) sums its few floats over all clusters in
+// cluster order (and, data parallel, exchanges that slice with the peer GPUs' same reducer over NVLink) -> grid barrier ->
+// everybody reads the totals.  All replicas then apply the identical clip + Adam update, so they never diverge.
+template <int NT1, bool DIST, bool WIDE>
 __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant__ PpoArgs a) {
     extern __shared__ __align__(16) float sm[];
+    if (WIDE && a.result[3] != 0) return;     // an earlier epoch's launch hit the target_kl stop: nothing left to do
     const float nu = a.nu_dev ? *a.nu_dev : a.nu;
+    const int cluster_id = WIDE ? (int)(blockIdx.x / NCTA) : 0;
+    const int ncl = WIDE ? a.ncl : 1;
+    // rows of a minibatch this cluster takes: [cluster_id * Bc, (cluster_id + 1) * Bc) clipped to the minibatch
+    const int Bc = WIDE ? ((a.B + ncl - 1) / ncl + RB - 1) / RB * RB : 0;
+    auto range_lo = [&](int Bn) { return WIDE ? min(cluster_id * Bc, Bn) : 0; };
+    auto range_len = [&](int Bn) { return WIDE ? max(min((cluster_id + 1) * Bc, Bn) - cluster_id * Bc, 0) : Bn; };
     const int LDX = a.DP, KP = a.KP, D = a.D;
     // payload of the pair exchange: gradient fragments + the five loss partial sums (thread 0)
     constexpr int NP = (NTW2 * 4 + NT1 * 4 + 4 + 1 + 5 + 3) / 4 * 4;
@@ -426,13 +438,18 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
     struct Cursor { int epoch, mb, c0; };
     auto cur_valid = [&](const Cursor& c) { return c.epoch < a.n_epochs; };
     auto cur_bn = [&](const Cursor& c) { return min(a.B, a.N - c.mb * a.B); };
+    auto cur_len = [&](const Cursor& c) { return range_len(cur_bn(c)); };
+    auto cur_skip_empty = [&](Cursor c) {      // (wide mode) minibatches in which this cluster has no rows
+        while (cur_valid(c) && cur_len(c) == 0) { if (++c.mb >= a.steps_per_epoch) { c.mb = 0; ++c.epoch; } }
+        return c;
+    };
     auto cur_next = [&](Cursor c) {
         c.c0 += RB;
-        if (c.c0 >= cur_bn(c)) { c.c0 = 0; if (++c.mb >= a.steps_per_epoch) { c.mb = 0; ++c.epoch; } }
+        if (c.c0 >= cur_len(c)) { c.c0 = 0; if (++c.mb >= a.steps_per_epoch) { c.mb = 0; ++c.epoch; } c = cur_skip_empty(c); }
         return c;
     };
     auto fetch_chunk = [&](const Cursor& c, int buf) {   // called by thread 0 only
-        const size_t p = (size_t)c.epoch * a.N + (size_t)c.mb * a.B + c.c0 + RBH * half;   // streams carry RB rows of tail padding
+        const size_t p = (size_t)c.epoch * a.N + (size_t)c.mb * a.B + range_lo(cur_bn(c)) + c.c0 + RBH * half;   // streams carry RB rows of tail padding
         const uint32_t xb = RBH * LDX * 4, sb = RBH * 8 * 4, ab = (role == 0) ? RBH * AP * 4 : 0;
         fence_proxy_async();   // earlier generic-proxy accesses to this buffer are ordered before the async-proxy writes
         mbar_expect_tx(&BAR[buf], xb + sb + ab);
@@ -441,11 +458,12 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
         if (role == 0) bulk_g2s(ACT + buf * RBH * AMAX, a.as + p * AP, ab, &BAR[buf]);
     };
 
-    Cursor cur = {0, 0, 0};
+    Cursor cur = cur_skip_empty(Cursor{0, 0, 0});
     int q = 0;                                   // running chunk counter (buffer parity / mbarrier phase)
-    if (working && tid == 0) fetch_chunk(cur, 0);
+    if (working && tid == 0 && cur_valid(cur)) fetch_chunk(cur, 0);
 
     int step = 0, early_stop_epoch = a.n_epochs;
+    bool kl_stopped = false;
     double epoch_kl_sum = 0.0;
     bool stop_all = false;
     const bool timed = (a.timing != nullptr) && tid == 0 && working;
@@ -505,10 +523,11 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                                  pay_remote + (uint32_t)(v4 * NTT * 16)),
                              "f"(x), "f"(y), "f"(z), "f"(w), "r"(pbar_remote) : "memory");
             };
+            const int len = range_len(Bn);           // rows of this minibatch that THIS cluster processes
             if (working) {
-                for (int c0 = 0; c0 < Bn; c0 += RB, ++q) {
-                    const bool last_chunk = (c0 + RB >= Bn);
-                    const int rows = min(max(min(RB, Bn - c0) - RBH * half, 0), RBH);   // valid rows of THIS CTA's half
+                for (int c0 = 0; c0 < len; c0 += RB, ++q) {
+                    const bool last_chunk = (c0 + RB >= len);
+                    const int rows = min(max(min(RB, len - c0) - RBH * half, 0), RBH);   // valid rows of THIS CTA's half
                     const int buf = q & 1;
                     const float* Xc = X + buf * RBH * LDX;
                     float* Rc = ROWF + buf * RBH * 8;
@@ -865,6 +884,17 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                     }
                     ICRL_MARK(7)
                 }  // chunks
+                if (WIDE && len == 0) {
+                    // no rows of this minibatch fall to this cluster: it still takes part in every exchange (with zeros)
+                    __syncthreads();
+                    if (tid == 0) {
+                        mbar_expect_tx(&BAR[2], (uint32_t)(PAY_V4 * NTT * 16));
+                        mbar_expect_tx(&BAR[3], (uint32_t)(NCTA * 8));
+                    }
+#pragma unroll
+                    for (int i = 0; i < NTW2; ++i) st4(i, 0.f, 0.f, 0.f, 0.f);
+                    st4(NTW2 + NT1, 0.f, 0.f, 0.f, 0.f);
+                }
             }      // working
 
             // ---- (1) block-reduce the five loss partial sums of this CTA's rows
@@ -944,9 +974,129 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                     const float4 x = ld4(v4++), y = ld4(v4++);
                     g_s += x.x; tot[0] += x.y; tot[1] += x.z; tot[2] += x.w; tot[3] += y.x; tot[4] += y.y;
                 }
-                // ---- (3) data parallel: all-reduce the pair sums across the ranks' matching CTAs over NVLink peer memory
+                // ---- (3w) wide mode: sum the pair sums of all clusters (and of all ranks) -- see the kernel's header comment
                 bool exchanged = false;
-                if (DIST && a.world > 1) {
+                if constexpr (WIDE) {
+                    constexpr int F = NTW2 * 4 + NT1 * 4 + 4 + 1 + 5;       // gradient floats + loss sums owned by a thread
+                    auto G = [&](int k) -> float& {                           // k is a compile-time constant at every use
+                        if (k < NTW2 * 4) return g_w2[k >> 2][k & 3];
+                        k -= NTW2 * 4;
+                        if (k < NT1 * 4) return g_w1[k >> 2][k & 3];
+                        k -= NT1 * 4;
+                        if (k < 4) return g_hw[k];
+                        k -= 4;
+                        if (k == 0) return g_s;
+                        return tot[k - 1];
+                    };
+                    // grid-wide barrier among the CTAs of this trunk (2 per cluster): arrival counter + acquire spin
+                    auto wide_barrier = [&](int which) {
+                        __syncthreads();
+                        if (tid == 0) {
+                            unsigned int* ctr = a.wide_sync + role;
+                            const unsigned int target = (unsigned int)(2 * step + which + 1) * (unsigned int)(2 * ncl);
+                            __threadfence();
+                            atomicAdd(ctr, 1u);
+                            if (*(volatile float*)&XCH[31] == 0.f) {
+                                const long long t0 = clock64();
+                                for (;;) {
+                                    unsigned int v;
+                                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+                                    if ((int)(v - target) >= 0) break;
+                                    if (clock64() - t0 > 4000000000LL) { XCH[31] = 1.f; break; }   // ~2 s: clusters not co-resident
+                                }
+                            }
+                        }
+                        __syncthreads();
+                    };
+                    const int nred = 2 * ncl;                      // reducers of a trunk: (cluster, half)
+                    const int S = (F + nred - 1) / nred;           // floats per reducer (<= WIDE_SMAX, checked by the host)
+                    const int rid = cluster_id * 2 + half;
+                    if (half == 0) {
+                        float* mine = a.wide_part + (((size_t)role * ncl + cluster_id) * F) * NTT + tid;
+#pragma unroll
+                        for (int k = 0; k < F; ++k) __stcg(mine + (size_t)k * NTT, G(k));
+                    }
+                    wide_barrier(0);
+                    {
+                        float rs[WIDE_SMAX];
+                        const float* pbase = a.wide_part + ((size_t)role * ncl * F) * NTT + tid;
+#pragma unroll
+                        for (int kk = 0; kk < WIDE_SMAX; ++kk) {
+                            rs[kk] = 0.f;
+                            const int k = rid * S + kk;
+                            if (kk < S && k < F) {
+                                float acc = 0.f;
+#pragma unroll 8
+                                for (int c = 0; c < ncl; ++c) acc += __ldcg(pbase + ((size_t)c * F + k) * NTT);   // cluster order
+                                rs[kk] = acc;
+                            }
+                        }
+                        if (DIST && a.world > 1) {
+                            // data parallel: the same reducer of every rank holds the same slice -> one-hop exchange of
+                            // {f0, f1, f2, seq ^ hash} words over NVLink peer memory, summed in rank order
+                            const unsigned int want = a.flag_base + (unsigned int)step + 1u;
+                            auto tag = [&](unsigned int x, unsigned int y, unsigned int z) {
+                                return want ^ ((x ^ __funnelshift_l(y, y, 11) ^ __funnelshift_l(z, z, 22)) * 0x9E3779B1u);
+                            };
+                            auto slab = [&](float* base, int src) {
+                                return reinterpret_cast<uint4*>(base) +
+                                       ((((size_t)parity * ICRL_PPO_MAX_RANKS + src) * WIDE_MAXCTA + (cluster_id * NCTA + crank)) * 2) * NTT + tid;
+                            };
+                            const int nw = S > 3 ? 2 : 1;
+                            for (int pr = 0; pr < a.world; ++pr) {
+                                uint4* dst = slab(a.recv[pr], a.rank);
+                                const unsigned int x0 = __float_as_uint(rs[0]), x1 = __float_as_uint(rs[1]), x2 = __float_as_uint(rs[2]);
+                                dst[0] = make_uint4(x0, x1, x2, tag(x0, x1, x2));
+                                if (nw > 1) {
+                                    const unsigned int y0 = __float_as_uint(rs[3]), y1 = __float_as_uint(rs[4]), y2 = __float_as_uint(rs[5]);
+                                    dst[NTT] = make_uint4(y0, y1, y2, tag(y0, y1, y2));
+                                }
+                            }
+                            uint4 x[2 * ICRL_PPO_MAX_RANKS];
+                            const long long tstart = clock64();
+                            for (;;) {
+                                bool ok = true;
+#pragma unroll
+                                for (int j = 0; j < 2 * ICRL_PPO_MAX_RANKS; ++j)
+                                    if ((j >> 1) < a.world && (j & 1) < nw) {
+                                        const uint4* src = slab(a.recv[a.rank], j >> 1) + (j & 1) * NTT;
+                                        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                                     : "=r"(x[j].x), "=r"(x[j].y), "=r"(x[j].z), "=r"(x[j].w)
+                                                     : "l"(src) : "memory");
+                                    }
+#pragma unroll
+                                for (int j = 0; j < 2 * ICRL_PPO_MAX_RANKS; ++j)
+                                    if ((j >> 1) < a.world && (j & 1) < nw) ok = ok && (x[j].w == tag(x[j].x, x[j].y, x[j].z));
+                                if (ok) break;
+                                if (clock64() - tstart > 4000000000LL) { XCH[31] = 1.f; break; }   // ~2 s: a peer is gone
+                            }
+#pragma unroll
+                            for (int kk = 0; kk < WIDE_SMAX; ++kk) rs[kk] = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 2 * ICRL_PPO_MAX_RANKS; ++j)
+                                if ((j >> 1) < a.world && (j & 1) < nw) {                    // j ascends rank-major: rank order
+                                    rs[3 * (j & 1) + 0] += __uint_as_float(x[j].x);
+                                    rs[3 * (j & 1) + 1] += __uint_as_float(x[j].y);
+                                    rs[3 * (j & 1) + 2] += __uint_as_float(x[j].z);
+                                }
+                        }
+                        float* red = a.wide_red + ((size_t)role * F) * NTT + tid;
+#pragma unroll
+                        for (int kk = 0; kk < WIDE_SMAX; ++kk) {
+                            const int k = rid * S + kk;
+                            if (kk < S && k < F) __stcg(red + (size_t)k * NTT, rs[kk]);
+                        }
+                    }
+                    wide_barrier(1);
+                    {
+                        const float* red = a.wide_red + ((size_t)role * F) * NTT + tid;
+#pragma unroll
+                        for (int k = 0; k < F; ++k) G(k) = __ldcg(red + (size_t)k * NTT);
+                    }
+                    exchanged = true;
+                }
+                // ---- (3) data parallel: all-reduce the pair sums across the ranks' matching CTAs over NVLink peer memory
+                if (!WIDE && DIST && a.world > 1) {
                     // ---- (3a) 4 / 8 ranks: reduce-scatter + all-gather, both with self-validating words.
                     // The direct scheme below makes every thread read W full gradient copies one after the other (W x 2
                     // dependent L2 round trips, which is what made the exchange cost grow linearly with W).  Here the
@@ -1128,7 +1278,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                     else if (want_rsag && a.world == 4) { rsag(std::integral_constant<int, 4>{}); exchanged = true; }
                     else if (want_rsag && a.world == 2) { rsag(std::integral_constant<int, 2>{}); exchanged = true; }
                 }
-                if (DIST && a.world > 1 && !exchanged) {
+                if (!WIDE && DIST && a.world > 1 && !exchanged) {
                     // ---- (3b) any other world size: direct exchange.  "LL" protocol (as NCCL's low-latency path): every 16-byte store carries two values and two copies of
                     // this step's sequence number, so the data validates itself -- no fence, no separate flag, no barrier:
                     // the exchange costs one NVLink store latency.  (A torn 16-byte store is still two self-validating
@@ -1235,14 +1385,14 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                 pl = pl + nu * (red[1] * invB);
                 pl = pl / (1.f + nu);
                 kl_step = red[3] * invB;
-                if (tid == 0 && half == 0) {
+                if (tid == 0 && half == 0 && cluster_id == 0) {
                     a.stats[so + 0] = pl;
                     a.stats[so + 1] = red[2] * invB;
                     a.stats[so + 4] = -(red[4] * invB);
                     a.stats[so + 5] = kl_step;
                 }
             } else if (working) {
-                if (tid == 0 && half == 0) a.stats[so + (role == 1 ? 2 : 3)] = red[0] * invB;
+                if (tid == 0 && half == 0 && cluster_id == 0) a.stats[so + (role == 1 ? 2 : 3)] = red[0] * invB;
             }
             ICRL_MARK(8)
 
@@ -1254,7 +1404,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                 ++epoch_steps;
                 const bool last_of_epoch = (mb == a.steps_per_epoch - 1);
                 if (last_of_epoch && a.has_target_kl && (epoch_kl_sum / epoch_steps) > 1.5 * a.target_kl) stop_flag = 1.f;
-                if (a.max_steps > 0 && step + 1 >= a.max_steps) stop_flag = 2.f;
+                if (a.max_steps > 0 && (WIDE ? a.epoch_base * a.steps_per_epoch : 0) + step + 1 >= a.max_steps) stop_flag = 2.f;
             }
             if (tid < ncta && working) {
                 uint32_t ra, rb;
@@ -1271,7 +1421,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
             const float stop_rx = XCH[(parity * 8 + 0) * 2 + 1];
             const float total_norm = sqrtf(total_ss);
             const float clip_coef = fminf(a.max_grad_norm / (total_norm + 1e-6f), 1.0f);
-            if (crank == 0 && tid == 0) {
+            if (crank == 0 && tid == 0 && cluster_id == 0) {
                 a.stats[so + 7] = total_norm;
                 a.stats[so + 6] = 0.f;   // total loss is assembled on the host from the parts (needs all three CTAs)
             }
@@ -1328,7 +1478,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                 }
             }
             ICRL_MARK(10)
-            if (stop_rx == 1.f) { early_stop_epoch = epoch; stop_all = true; }
+            if (stop_rx == 1.f) { early_stop_epoch = (WIDE ? a.epoch_base : 0) + epoch; stop_all = true; kl_stopped = true; }
             if (stop_rx == 2.f) { stop_all = true; }
             // (the next chunk's leading __syncthreads orders these shared-memory weight updates before their first use)
         }  // minibatches
@@ -1341,7 +1491,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
 #undef ICRL_MARK
 
     // ---- write back parameters and moments (owner threads of the first CTA of each pair; the second holds identical copies)
-    if (working && half == 0) {
+    if (working && half == 0 && cluster_id == 0) {
 #pragma unroll
         for (int nt = 0; nt < NTW2; ++nt)
 #pragma unroll
@@ -1367,9 +1517,14 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
             a.params[f] = *slot; a.adam_m[f] = m_s; a.adam_v[f] = v_s;
         }
     }
-    if (crank == 0 && tid == 0) {
-        a.result[0] = early_stop_epoch;
-        a.result[1] = step;
+    if (crank == 0 && tid == 0 && cluster_id == 0) {
+        if (WIDE) {        // one launch per epoch: the host presets result[0] = n_epochs, the steps accumulate over the launches
+            if (stop_all) { a.result[3] = 1; if (kl_stopped) a.result[0] = early_stop_epoch; }
+            a.result[1] = a.result[1] + step;
+        } else {
+            a.result[0] = early_stop_epoch;
+            a.result[1] = step;
+        }
     }
     // an exchange wait of ANY CTA hit its bound (lost cluster peer / data-parallel rank): the host zeroes result[2] before the
     // launch and raises when it comes back set (the parameters of such a launch are not valid)
@@ -1379,34 +1534,119 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
 
 // ---------------------------------------------------------------- host side
 template <int NT1>
-static int launch_ppo(const PpoArgs& a, cudaStream_t st) {
-    auto kern = a.world > 1 ? ppo_train_kernel<NT1, true> : ppo_train_kernel<NT1, false>;
-    constexpr int NP = (NTW2 * 4 + NT1 * 4 + 4 + 1 + 5 + 3) / 4 * 4;
-    const PpoSmem L = ppo_smem_layout(a.DP, NP);
+constexpr int ppo_pay_floats() { return (NTW2 * 4 + NT1 * 4 + 4 + 1 + 5 + 3) / 4 * 4; }
+template <int NT1>
+constexpr int ppo_frag_floats() { return NTW2 * 4 + NT1 * 4 + 4 + 1 + 5; }     // F: floats a thread owns in the exchanges
+
+template <int NT1, bool WIDE>
+static int launch_cfg(const PpoArgs& a, cudaStream_t st, int n_clusters, cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr,
+                      void (**kern_out)(const PpoArgs)) {
+    void (*kern)(const PpoArgs) = WIDE ? (a.world > 1 ? ppo_train_kernel<NT1, true, true> : ppo_train_kernel<NT1, false, true>)
+                                       : (a.world > 1 ? ppo_train_kernel<NT1, true, false> : ppo_train_kernel<NT1, false, false>);
+    const PpoSmem L = ppo_smem_layout(a.DP, ppo_pay_floats<NT1>());
     if (L.total_bytes > 227 * 1024) {
         set_error("obs_dim %d needs %d bytes of shared memory (> 227 KB)", a.D, L.total_bytes);
         return ICRL_EUNSUPPORTED;
     }
     ICRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes));
-    // one cluster of 6 CTAs: a CTA pair per trunk (pi, vf, cvf)
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(NCTA);
-    cfg.blockDim = dim3(NTT);
-    cfg.dynamicSmemBytes = L.total_bytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
+    *cfg = cudaLaunchConfig_t{};
+    cfg->gridDim = dim3(NCTA * n_clusters);
+    cfg->blockDim = dim3(NTT);
+    cfg->dynamicSmemBytes = L.total_bytes;
+    cfg->stream = st;
+    attr[0].id = cudaLaunchAttributeClusterDimension;      // clusters of 6 CTAs: a CTA pair per trunk (pi, vf, cvf)
     attr[0].val.clusterDim.x = NCTA;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg->attrs = attr;
+    cfg->numAttrs = 1;
+    *kern_out = kern;
+    return 0;
+}
+
+template <int NT1>
+static int launch_ppo(const PpoArgs& a, cudaStream_t st) {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    void (*kern)(const PpoArgs);
+    if (int rc = launch_cfg<NT1, false>(a, st, 1, &cfg, attr, &kern)) return rc;
     const cudaError_t err = cudaLaunchKernelEx(&cfg, kern, a);
     if (err != cudaSuccess) {
         set_error("ppo_train_kernel launch failed: %s", cudaGetErrorString(err));
         return (int)err;
     }
     count_launch();
+    return 0;
+}
+
+// how many 6-CTA clusters of the wide kernel can be resident at once on this device (all of them spin on grid barriers, so
+// the launch must never exceed it); cached per (device, instantiation)
+template <int NT1>
+static int wide_max_clusters(const PpoArgs& a, cudaStream_t st, int* out) {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    void (*kern)(const PpoArgs);
+    if (int rc = launch_cfg<NT1, true>(a, st, 1, &cfg, attr, &kern)) return rc;
+    cfg.gridDim = dim3(NCTA * 32);
+    int n = 0;
+    ICRL_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    *out = n;
+    return 0;
+}
+
+// wide mode: one launch per epoch -- gather that epoch's minibatch-ordered streams, its per-step statistics, then the
+// many-cluster kernel.  The device decides the target_kl stop (result[3]); later launches return at once.
+template <int NT1>
+static int launch_ppo_wide(PpoArgs a, cudaStream_t st, int n_clusters, float* xs, float* as, float* ss, float* advstats) {
+    constexpr int F = ppo_frag_floats<NT1>();
+    void *part, *sync;
+    int rc;
+    const size_t part_floats = ((size_t)3 * n_clusters * F + (size_t)3 * F) * NTT;
+    if ((rc = device_scratch(SLOT_PPO4, part_floats * 4, &part))) return rc;
+    if ((rc = device_scratch(SLOT_PPO5, 64, &sync))) return rc;
+    const int n_epochs = a.n_epochs, spe = a.steps_per_epoch;
+    const int* perm = a.perm;
+    float* stats = a.stats;
+    const double* advsums = a.advsums;
+    const long long step_before = a.step_before;
+    const unsigned int flag_base = a.flag_base;
+    a.ncl = n_clusters;
+    a.n_epochs_total = n_epochs;
+    a.wide_part = (float*)part;
+    a.wide_red = (float*)part + (size_t)3 * n_clusters * F * NTT;
+    a.wide_sync = (unsigned int*)sync;
+    a.xs = xs; a.as = as; a.ss = ss; a.advstats = advstats;
+    {   // result[0] = n_epochs unless a launch stops early
+        const int32_t init[4] = {n_epochs, 0, 0, 0};
+        ICRL_CUDA(cudaMemcpyAsync(a.result, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    }
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    void (*kern)(const PpoArgs);
+    if ((rc = launch_cfg<NT1, true>(a, st, n_clusters, &cfg, attr, &kern))) return rc;
+    const long long n_alloc = (long long)a.N + RB;
+    const long long blocks = (n_alloc + 7) / 8;
+    const int ggrid = (int)(blocks < 8LL * sm_count() ? blocks : 8LL * sm_count());
+    for (int e = 0; e < n_epochs; ++e) {
+        a.n_epochs = 1;
+        a.epoch_base = e;
+        a.perm = perm + (size_t)e * a.N;
+        a.stats = stats + (size_t)e * spe * ICRL_PPO_STATS_PER_STEP;
+        a.advsums = advsums ? advsums + (size_t)e * spe * 4 : nullptr;
+        a.step_before = step_before + (long long)e * spe;
+        a.flag_base = flag_base + (unsigned int)(e * spe);
+        ppo_gather_kernel<<<ggrid, 256, 0, st>>>(a, xs, as, ss, (long long)a.N, n_alloc);
+        ICRL_LAUNCH_CHECK();
+        ppo_stats_kernel<<<spe, 128, 0, st>>>(ss, advstats, a.N, a.B, spe, a.beta1, a.beta2, a.lr, a.step_before, a.advsums);
+        ICRL_LAUNCH_CHECK();
+        ICRL_CUDA(cudaMemsetAsync(sync, 0, 64, st));
+        const cudaError_t err = cudaLaunchKernelEx(&cfg, kern, a);
+        if (err != cudaSuccess) {
+            set_error("wide ppo_train_kernel launch failed: %s", cudaGetErrorString(err));
+            return (int)err;
+        }
+        count_launch();
+    }
     return 0;
 }
 
@@ -1459,9 +1699,38 @@ static int ppo_train_impl(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, fl
     }
     cudaStream_t st = (cudaStream_t)stream;
     ICRL_CUDA(cudaMemsetAsync(result, 0, 4 * sizeof(int32_t), st));
+    const int n_tiles = a.KP / 8;                 // n-tiles of dW1; each warp owns every second one
+    const int nt1 = (n_tiles + 1) / 2;
+    if (nt1 > 8) {
+        icrl::set_error("obs_dim %d too large for the PPO kernel (max 128)", a.D);
+        return ICRL_EUNSUPPORTED;
+    }
+    // large batches run on many clusters (ICRL_PPO_WIDE=0/1 forces the choice, ICRL_PPO_WIDE_CLUSTERS caps the cluster count)
+    bool wide = a.B >= icrl::WIDE_MIN_BATCH;
+    if (const char* m = getenv("ICRL_PPO_WIDE")) wide = atoi(m) != 0;
+    int n_clusters = 1;
+    if (wide) {
+        int cap = 0;
+        if (nt1 <= 1) rc = icrl::wide_max_clusters<1>(a, st, &cap);
+        else if (nt1 <= 2) rc = icrl::wide_max_clusters<2>(a, st, &cap);
+        else if (nt1 <= 4) rc = icrl::wide_max_clusters<4>(a, st, &cap);
+        else rc = icrl::wide_max_clusters<8>(a, st, &cap);
+        if (rc) return rc;
+        if (cap > icrl::WIDE_MAXCTA / icrl::NCTA) cap = icrl::WIDE_MAXCTA / icrl::NCTA;
+        const int useful = (a.B + icrl::RB - 1) / icrl::RB;            // one 64-row chunk per cluster at least
+        n_clusters = cap < useful ? cap : useful;
+        if (const char* m = getenv("ICRL_PPO_WIDE_CLUSTERS")) {          // tests: exactly this many clusters (some may stay empty)
+            const int c = atoi(m);
+            if (c > 0) n_clusters = c < cap ? c : cap;
+        }
+        const int nt1r = nt1 <= 1 ? 1 : nt1 <= 2 ? 2 : nt1 <= 4 ? 4 : 8;
+        const int F = icrl::NTW2 * 4 + nt1r * 4 + 4 + 1 + 5;
+        if (n_clusters < 1 || 2 * n_clusters * icrl::WIDE_SMAX < F) wide = false;   // too few clusters to spread the reduction
+    }
     {
-        const int total_steps = a.n_epochs * a.steps_per_epoch;
-        const long long n_rows = (long long)a.n_epochs * a.N, n_alloc = n_rows + icrl::RB;
+        const int epochs_alloc = wide ? 1 : a.n_epochs;           // wide mode stages one epoch at a time
+        const int total_steps = epochs_alloc * a.steps_per_epoch;
+        const long long n_rows = (long long)epochs_alloc * a.N, n_alloc = n_rows + icrl::RB;
         const int aw = a.is_discrete ? 1 : a.A;
         a.AP = (aw + 3) / 4 * 4;
         void *xs, *as, *ss, *advstats;
@@ -1469,6 +1738,12 @@ static int ppo_train_impl(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, fl
         if ((rc = icrl::device_scratch(icrl::SLOT_PPO1, (size_t)total_steps * 8 * sizeof(float), &advstats))) return rc;
         if ((rc = icrl::device_scratch(icrl::SLOT_PPO2, (size_t)n_alloc * a.AP * 4, &as))) return rc;
         if ((rc = icrl::device_scratch(icrl::SLOT_PPO3, (size_t)n_alloc * 8 * 4, &ss))) return rc;
+        if (wide) {
+            if (nt1 <= 1) return icrl::launch_ppo_wide<1>(a, st, n_clusters, (float*)xs, (float*)as, (float*)ss, (float*)advstats);
+            if (nt1 <= 2) return icrl::launch_ppo_wide<2>(a, st, n_clusters, (float*)xs, (float*)as, (float*)ss, (float*)advstats);
+            if (nt1 <= 4) return icrl::launch_ppo_wide<4>(a, st, n_clusters, (float*)xs, (float*)as, (float*)ss, (float*)advstats);
+            return icrl::launch_ppo_wide<8>(a, st, n_clusters, (float*)xs, (float*)as, (float*)ss, (float*)advstats);
+        }
         const long long blocks = (n_alloc + 7) / 8;
         const int grid = (int)(blocks < 8LL * icrl::sm_count() ? blocks : 8LL * icrl::sm_count());
         icrl::ppo_gather_kernel<<<grid, 256, 0, st>>>(a, (float*)xs, (float*)as, (float*)ss, n_rows, n_alloc);
@@ -1483,16 +1758,10 @@ static int ppo_train_impl(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, fl
     const bool want_timing = getenv("ICRL_PPO_TIMING") != nullptr;
     if (want_timing && !timing_dev) cudaMalloc(&timing_dev, 128 * sizeof(unsigned long long));
     a.timing = want_timing ? timing_dev : nullptr;
-    const int n_tiles = a.KP / 8;                 // n-tiles of dW1; each warp owns every second one
-    const int nt1 = (n_tiles + 1) / 2;
     if (nt1 <= 1) rc = icrl::launch_ppo<1>(a, st);
     else if (nt1 <= 2) rc = icrl::launch_ppo<2>(a, st);
     else if (nt1 <= 4) rc = icrl::launch_ppo<4>(a, st);
-    else if (nt1 <= 8) rc = icrl::launch_ppo<8>(a, st);
-    else {
-        icrl::set_error("obs_dim %d too large for the PPO kernel (max 128)", a.D);
-        return ICRL_EUNSUPPORTED;
-    }
+    else rc = icrl::launch_ppo<8>(a, st);
     if (rc == 0 && want_timing) {   // profiling aid: per-phase cycles of thread 0 of each trunk CTA (synchronises!)
         unsigned long long h[128];
         cudaStreamSynchronize(st);

@@ -177,6 +177,7 @@ class DeviceLearner:
         if comm is not None and comm.world > 1:
             self.advsums = th.zeros(w.n_epochs * self.steps_per_epoch, 4, dtype=th.float64, device=d)
             self.cost_mean = th.zeros(1, device=d)
+            self.shard_k2(seed)
         self.refresh_behaviour()
         self.new_permutations(seed)
 
@@ -291,12 +292,35 @@ class DeviceLearner:
             iterations=w.backward_iters, importance_sampling=1, per_step_is=int(w.per_step_is), train_gail_lambda=0,
             eps=float(cn.eps), regularizer_coeff=float(w.cn_reg), target_kl_old_new=float(cn.target_kl_old_new),
             target_kl_new_old=float(cn.target_kl_new_old), lr=float(g["lr"]), adam_beta1=0.9, adam_beta2=0.999,
-            adam_eps=float(g["eps"]))
+            adam_eps=float(g["eps"]), batch_size=0, perm=None)
         metrics = _lib.CnTrainMetrics()
         step = C.c_int64(cn.optimizer.step_count)
-        _lib.check(_lib.lib().icrl_cn_train(
-            C.byref(cn._get_desc()), C.byref(cfg), _lib.ptr(self.nom_obs), 0, _lib.ptr(self.nom_acs), w.nominal_rows,
-            _lib.ptr(self.offsets), self.n_episodes, _lib.ptr(self.exp_obs), 0, _lib.ptr(self.exp_acs), w.expert_rows,
-            _lib.ptr(cn._adam_m), _lib.ptr(cn._adam_v), C.byref(step), C.byref(metrics), _lib.current_stream()))
+        args = (C.byref(cn._get_desc()), C.byref(cfg), _lib.ptr(self.nom_obs), 0, _lib.ptr(self.nom_acs), w.nominal_rows,
+                _lib.ptr(self.offsets), self.n_episodes, _lib.ptr(self.exp_obs), 0, _lib.ptr(self.exp_acs),
+                self.exp_obs.shape[0], _lib.ptr(cn._adam_m), _lib.ptr(cn._adam_v), C.byref(step), C.byref(metrics))
+        cc = getattr(cn, "comm", None)
+        if cc is None or cc.world == 1:
+            _lib.check(_lib.lib().icrl_cn_train(*args, _lib.current_stream()))
+        else:
+            # data parallel: this rank's own nominal episodes, its slice of the expert batch (set up in shard_k2)
+            d = cc.descriptor(w.nominal_rows * cc.world, self.exp_rows_global, self.n_episodes * cc.world,
+                              self.n_episodes * cc.rank)
+            _lib.check(_lib.lib().icrl_cn_train_dist(*args, C.byref(d), _lib.current_stream()))
+            cc.advance(w.backward_iters)
         cn.optimizer.step_count = int(step.value)
         self.last_cn_metrics = metrics
+
+    def shard_k2(self, seed: int):
+        """Data-parallel K2: every rank keeps nominal episodes of its own (seed) and an even slice of the
+        replicated expert batch; the constraint net's exchange buffers are set up here (outside the timed region)."""
+        w, cn, comm = self.w, self.cn, self.comm
+        if comm is None or comm.world == 1 or not w.nominal_rows:
+            return
+        cn.enable_data_parallel(max_episodes=max(1024, 2 * self.n_episodes * comm.world))
+        _, _, no, na, _ = synth_demos(w, seed)
+        self.nom_obs = th.from_numpy(no).to(self.dev)
+        self.nom_acs = th.from_numpy(na.reshape(-1) if w.is_discrete else na).to(self.dev)
+        n = self.exp_obs.shape[0]
+        self.exp_rows_global = n
+        lo, hi = n * comm.rank // comm.world, n * (comm.rank + 1) // comm.world
+        self.exp_obs, self.exp_acs = self.exp_obs[lo:hi].contiguous(), self.exp_acs[lo:hi].contiguous()

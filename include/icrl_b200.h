@@ -43,6 +43,9 @@ const char* icrl_last_error(void);
 int64_t icrl_launch_count(void);
 /* device properties the host side sizes grids with; returns 0 and fills *sm_count / *cc (e.g. 100) */
 int icrl_device_info(int32_t* sm_count, int32_t* cc);
+/* measured arithmetic peaks of the current device in TFLOP/s (bench.py's compute rooflines; synchronous, ~50 ms):
+ * tflops2[0] = FP32 FFMA, tflops2[1] = mma.sync.m16n8k8 TF32 with fp32 accumulate (K4 issues three per fp32-class product) */
+int icrl_measure_peaks(double* tflops2, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Constraint net description (ConstraintNet.__init__ state, icrl/constraint_net.py:15-99).
@@ -185,6 +188,14 @@ int icrl_dual_gae_host(const float* rewards, const float* reward_values, const f
  * `perm` refer to the reference's env-major flattening (row = e*T + t, buffers.py:52-65,598-603) and are
  * translated on the device, so no transposed copy is ever made.  `perm` is int32 [n_epochs, T*E]: the
  * permutations numpy would draw (buffers.py:596), generated by the host so seeds stay compatible.
+ *
+ * Two regimes behind the same entry point (the reference allows any batch_size, None = the whole buffer, buffers.py:605-607):
+ *   batch_size <  2048  one persistent 6-CTA cluster (a CTA pair per trunk) runs all epochs: the dependent-step latency regime
+ *                       of the shipped configs (64 / 128 rows x 1 600 steps per rollout);
+ *   batch_size >= 2048  "wide": as many 6-CTA clusters as fit the device (24 on a B200) share every minibatch, one launch per
+ *                       epoch; per optimiser step the clusters' gradients are summed in cluster order through L2 between two
+ *                       grid-wide barriers and every cluster applies the same clip + Adam step to its replica.
+ * ICRL_PPO_WIDE=0/1 forces the choice, ICRL_PPO_WIDE_CLUSTERS=n the cluster count (tests).
  */
 typedef struct icrl_ppo_cfg {
     int32_t obs_dim, act_dim, is_discrete; /* act_dim = action dims (continuous) or number of actions (discrete) */
@@ -218,7 +229,8 @@ typedef struct icrl_ppo_data {
 /* per optimiser step, written to `step_stats` [n_epochs * steps_per_epoch, 8] device float32:
  * 0 policy_loss (pg_losses), 1 clip_fraction, 2 reward_value_loss, 3 cost_value_loss, 4 entropy_loss,
  * 5 approx_kl, 6 total loss, 7 grad-norm before clipping.  `result` is device int32[4]:
- * [0] early_stop_epoch (== n_epochs when no early stop), [1] optimiser steps taken, [2..3] reserved. */
+ * [0] early_stop_epoch (== n_epochs when no early stop), [1] optimiser steps taken, [2] != 0: an exchange wait inside the
+ * kernel hit its bound (lost cluster peer / data-parallel rank; the parameters of this call are not valid), [3] internal. */
 int64_t icrl_ppo_param_count(const icrl_ppo_cfg* cfg);
 int icrl_ppo_train(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* params, float* adam_m, float* adam_v,
                    int64_t adam_step_before, float* step_stats, int32_t* result, void* stream);
@@ -237,7 +249,8 @@ int icrl_ppo_train(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* pa
  * all-reduces one small table up front (icrl_ppo_local_advsums -> NCCL all-reduce -> icrl_ppo_dist.advsums).
  */
 #define ICRL_PPO_MAX_RANKS 8
-#define ICRL_PPO_RECV_BYTES (2 * ICRL_PPO_MAX_RANKS * 6 * 72 * 256 * 8) /* largest of the three layouts: [parity][src][cta of the 6-CTA cluster][slot pair][thread] {value, seq, value, seq} */
+#define ICRL_PPO_RECV_BYTES (32 * 1024 * 1024) /* covers the largest receive layout: the four single-cluster layouts (<= 14.2 MB, k4_common.cuh) and the
+                                                   many-cluster one [parity 2][src 8][CTA 192][2 words][256 threads] x 16 bytes = 25.2 MB */
 #define ICRL_PPO_FLAG_BYTES (2 * ICRL_PPO_MAX_RANKS * 4 * 4)             /* [parity][src][trunk] uint32 */
 
 int icrl_comm_alloc(int64_t bytes, void** dev_ptr, unsigned char* handle64);   /* zeroed device buffer + its IPC handle */

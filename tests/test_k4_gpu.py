@@ -119,6 +119,32 @@ def test_full_size_and_large_batch_match_reference(case):
                 assert abs(float(got[k]) - log[k]) <= 5e-4 * max(abs(log[k]), 1e-2), (k, float(got[k]), log[k])
 
 
+@pytest.mark.parametrize("case,clusters", [("hc", 5), ("ant", 6), ("lgw", 5), ("hc_klstop", 8), ("hc_vfclip", 7), ("point", 24),
+                                           ("hc_fullbatch", 3)])
+def test_wide_kernel_on_small_fixtures(case, clusters, monkeypatch):
+    """The many-cluster kernel forced onto the small fixtures (ICRL_PPO_WIDE=1): most clusters get no rows at all, so the
+    zero-row paths of every exchange, the per-epoch launches and the device-side KL stop across launches are exercised
+    against the same reference outputs."""
+    from icrl_b200 import logger
+    monkeypatch.setenv("ICRL_PPO_WIDE", "1")
+    monkeypatch.setenv("ICRL_PPO_WIDE_CLUSTERS", str(clusters))
+    d = load_golden(f"k4_{case}")
+    algo, hp, names = build_algo(d)
+    logger.configure()
+    np.random.seed(int(hp["numpy_seed"]))
+    algo.train()
+    err = max_param_err(params_of(algo, names), [d["p1." + n] for n in names])
+    assert err <= PARAM_RTOL, f"params after train(): {err}"
+    log = {k[4:]: float(v) for k, v in d.items() if k.startswith("log.")}
+    got = logger.Logger.CURRENT.name_to_value
+    assert int(got["train/early_stop_epoch"]) == int(log["train/early_stop_epoch"])
+    for k in ("train/policy_gradient_loss", "train/reward_value_loss", "train/cost_value_loss", "train/approx_kl", "train/loss"):
+        assert abs(float(got[k]) - log[k]) <= 2e-4 * max(abs(log[k]), 1e-2), (k, float(got[k]), log[k])
+    algo.train()
+    err = max_param_err(params_of(algo, names), [d["p2." + n] for n in names])
+    assert err <= 3 * PARAM_RTOL, f"params after second train(): {err}"
+
+
 def test_one_update_and_adam_state():
     """The north-star gate: parameters after ONE optimiser step <= 1e-4, plus the Adam moments themselves."""
     d = load_golden("k4_hc_fullbatch")
