@@ -244,6 +244,20 @@ __global__ void __launch_bounds__(256) cn_is_weights_kernel(CnCtrl* ctrl, const 
         }
         __threadfence_system();
         for (int r = 0; r < x.world; ++r) cn_st_release_sys(&x.hdr(r)->flags[1][x.rank], want);
+        // the logged is_mean / is_max / is_min are those of the LAST importance-weight evaluation, early stops included
+        // (constraint_net.py:171-177, 214-216): combine all ranks' statistics here rather than in the Adam kernel
+        const CnXHeader* h = x.hdr(x.rank);
+        double sw = 0.0, wmx = -INFINITY, wmn = INFINITY, wnan = 0.0;
+        const long long t0 = clock64();
+        for (int r = 0; r < x.world; ++r) {
+            while ((int)(cn_ld_acquire_sys(&h->flags[1][r]) - want) < 0) {
+                if (clock64() - t0 > 4000000000LL) { ctrl->error = 1; break; }
+            }
+            sw += h->wstat[r][0]; wmx = fmax(wmx, h->wstat[r][1]); wmn = fmin(wmn, h->wstat[r][2]); wnan += h->wstat[r][3];
+        }
+        ctrl->is_mean = (float)(sw / n_global);
+        ctrl->is_max = wnan > 0.0 ? NAN : (float)wmx;      // torch.max / min propagate NaN
+        ctrl->is_min = wnan > 0.0 ? NAN : (float)wmn;
         ctrl->stopped = ctrl->pending_stop;
         ctrl->ticket[1] = 0;
     }
@@ -444,7 +458,8 @@ __global__ void __launch_bounds__(128) cn_grad_kernel(const __grid_constant__ Cn
                 const float wi = per_step ? mean_w : w[idx ? (long long)idx[row0 + r] : row0 + r];
                 if (gail) {
                     const float l1 = fmaxf(logf(1.f - pr), -100.f);            // nn.BCELoss clamps log at -100
-                    st[ST_NLOG] += -l1; st[ST_NWLOG] += -l1;
+                    st[ST_NLOG] += logf(pr + eps);      // `unweighted_nominal_loss` is mean(log(p + eps)) in both modes (:211)
+                    st[ST_NWLOG] += -l1;                // BCE(p, 0)
                     dLdp = (l1 > -100.f ? 1.f / (1.f - pr) : 0.f) * inv_nn;
                 } else {
                     const float lg = logf(pr + eps);
@@ -648,22 +663,13 @@ __global__ void __launch_bounds__(256) cn_adam_kernel(CnCtrl* ctrl, const CnX x,
             nmax = fmax(nmax, h->stats[r][ST_NMAX]); nmin = fmin(nmin, h->stats[r][ST_NMIN]);
             emax = fmax(emax, h->stats[r][ST_EMAX]); emin = fmin(emin, h->stats[r][ST_EMIN]);
         }
-        // importance-weight statistics over all ranks' nominal rows (exchange 1 precedes exchange 2 on every rank)
-        double sw = 0.0, wmx = -INFINITY, wmn = INFINITY, wnan = 0.0;
-        for (int r = 0; r < x.world; ++r) {
-            sw += h->wstat[r][0]; wmx = fmax(wmx, h->wstat[r][1]); wmn = fmin(wmn, h->wstat[r][2]); wnan += h->wstat[r][3];
-            if (h->wstat[r][1] != h->wstat[r][1]) wnan += 1.0;
-        }
-        const float is_mean = (float)(sw / n_is_global);
-        ctrl->is_mean = is_mean;
-        ctrl->is_max = wnan > 0.0 ? NAN : (float)wmx;      // torch.max / min propagate NaN
-        ctrl->is_min = wnan > 0.0 ? NAN : (float)wmn;
+        const float is_mean = ctrl->is_mean;      // written by this iteration's cn_is_weights_kernel (all ranks' rows)
         const float mean_w = !(use_is && per_step) ? 1.f : (batch_mode ? ctrl->mean_w : is_mean);
         const double nn = n_nom_global, ne = n_exp_global;
         const float expert_loss = (float)(s[ST_ELOG] / ne), unweighted = (float)(s[ST_NLOG] / nn);
         float nominal_loss, reg_loss, loss;
         if (gail) {
-            nominal_loss = unweighted; reg_loss = 0.f;
+            nominal_loss = (float)(s[ST_NWLOG] / nn); reg_loss = 0.f;
             loss = nominal_loss + expert_loss;
         } else {
             nominal_loss = (use_is && per_step) ? mean_w * unweighted : (float)(s[ST_NWLOG] / nn);

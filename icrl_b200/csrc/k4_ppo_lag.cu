@@ -1052,33 +1052,30 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                                     dst[NTT] = make_uint4(y0, y1, y2, tag(y0, y1, y2));
                                 }
                             }
-                            uint4 x[2 * ICRL_PPO_MAX_RANKS];
-                            const long long tstart = clock64();
-                            for (;;) {
-                                bool ok = true;
-#pragma unroll
-                                for (int j = 0; j < 2 * ICRL_PPO_MAX_RANKS; ++j)
-                                    if ((j >> 1) < a.world && (j & 1) < nw) {
-                                        const uint4* src = slab(a.recv[a.rank], j >> 1) + (j & 1) * NTT;
-                                        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
-                                                     : "=r"(x[j].x), "=r"(x[j].y), "=r"(x[j].z), "=r"(x[j].w)
-                                                     : "l"(src) : "memory");
-                                    }
-#pragma unroll
-                                for (int j = 0; j < 2 * ICRL_PPO_MAX_RANKS; ++j)
-                                    if ((j >> 1) < a.world && (j & 1) < nw) ok = ok && (x[j].w == tag(x[j].x, x[j].y, x[j].z));
-                                if (ok) break;
-                                if (clock64() - tstart > 4000000000LL) { XCH[31] = 1.f; break; }   // ~2 s: a peer is gone
-                            }
+                            // ranks are polled one after the other (two words in flight): a few NVLink round trips per step are
+                            // noise next to a wide step, and the big polling arrays of the single-cluster schemes would cost
+                            // registers in the chunk loop
 #pragma unroll
                             for (int kk = 0; kk < WIDE_SMAX; ++kk) rs[kk] = 0.f;
-#pragma unroll
-                            for (int j = 0; j < 2 * ICRL_PPO_MAX_RANKS; ++j)
-                                if ((j >> 1) < a.world && (j & 1) < nw) {                    // j ascends rank-major: rank order
-                                    rs[3 * (j & 1) + 0] += __uint_as_float(x[j].x);
-                                    rs[3 * (j & 1) + 1] += __uint_as_float(x[j].y);
-                                    rs[3 * (j & 1) + 2] += __uint_as_float(x[j].z);
+                            const long long tstart = clock64();
+                            for (int src_rank = 0; src_rank < a.world; ++src_rank) {          // rank order: identical bits everywhere
+                                const uint4* src = slab(a.recv[a.rank], src_rank);
+                                uint4 x0, x1 = make_uint4(0u, 0u, 0u, 0u);
+                                for (;;) {
+                                    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                                 : "=r"(x0.x), "=r"(x0.y), "=r"(x0.z), "=r"(x0.w) : "l"(src) : "memory");
+                                    bool ok = (x0.w == tag(x0.x, x0.y, x0.z));
+                                    if (nw > 1) {
+                                        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                                     : "=r"(x1.x), "=r"(x1.y), "=r"(x1.z), "=r"(x1.w) : "l"(src + NTT) : "memory");
+                                        ok = ok && (x1.w == tag(x1.x, x1.y, x1.z));
+                                    }
+                                    if (ok) break;
+                                    if (clock64() - tstart > 4000000000LL) { XCH[31] = 1.f; break; }   // ~2 s: a peer is gone
                                 }
+                                rs[0] += __uint_as_float(x0.x); rs[1] += __uint_as_float(x0.y); rs[2] += __uint_as_float(x0.z);
+                                rs[3] += __uint_as_float(x1.x); rs[4] += __uint_as_float(x1.y); rs[5] += __uint_as_float(x1.z);
+                            }
                         }
                         float* red = a.wide_red + ((size_t)role * F) * NTT + tid;
 #pragma unroll
