@@ -1,18 +1,19 @@
-// K3 -- dual reward/cost GAE as a chunked, segmented reverse scan.
+// K3 -- dual reward/cost GAE as a single-pass, register-resident segmented reverse scan.
 // Replaces RolloutBufferWithCost._compute_returns_and_advantage x2
 // (stable_baselines3/common/buffers.py:493-552), a Python loop over n_steps.
 //
 // A_t = delta_t + c_t * A_{t+1} is an affine recurrence; `done` flags make it segmented (c_t = 0).
-// A CTA owns a group of adjacent env columns (32: every [T,E] access is a coalesced 128-byte row segment; 8: four
-// time sub-chunks share a warp) and its threads split the time axis into chunks:
-//   phase 1  each thread folds its chunk into an affine map (M, B):  A_lo = B + M * A_hi      (float64)
-//   phase 2  chunk maps are combined back-to-front through shared memory -> carry-in per chunk
-//   phase 3  the chunk is replayed with the reference's exact operation order and dtypes:
-//            delta in float32 (rounded per op, no FMA contraction), carry in float64, one rounding to
-//            float32 per stored advantage, returns = adv_f32 + value_f32.
-// Reward and cost scans run in the same thread (two independent dependency chains).
-// Roofline: 5 float reads + 4 float writes = 36 B per transition; HBM-bound.  Phase 3 re-reads the chunk,
-// which is served by L1/L2 for reference-sized buffers.
+// Every transition is read ONCE and written once (36 B, the algorithmic minimum):
+//   * a thread owns 8 consecutive steps of one env column and keeps their raw float32 inputs in registers (43 independent
+//     loads issued up front: the memory system sees all of them at once, the recurrence none);
+//   * it folds its 8 steps into an affine map (M, B):  A_lo = B + M * A_hi  (float64), per signal;
+//   * lane groups of a warp = consecutive 8-step blocks of the same columns -> warp-shuffle scan of the maps, warp aggregates
+//     meet in shared memory, a CTA window (NT / CG blocks of 8 steps) hands its carry to the next window (earlier in time);
+//   * the 8 steps are then replayed FROM REGISTERS with the reference's exact operation order and dtypes: delta in float32
+//     (rounded per op, no FMA contraction), carry in float64, one rounding to float32 per stored advantage,
+//     returns = adv_f32 + value_f32.
+// Reward and cost scans run in the same thread (two independent dependency chains).  CG adjacent columns per CTA: 8 (every
+// row access of a lane group is one full 32-byte sector) for wide buffers, 4 for narrow ones (twice the time slots per CTA).
 #include "common.cuh"
 
 namespace icrl {
@@ -30,145 +31,140 @@ struct Step {
     double coef;   // c_t
 };
 
-// delta_t and c_t for one signal at time t, exactly as numpy evaluates buffers.py:528-537.
-__device__ __forceinline__ Step gae_step(const float* __restrict__ rew, const float* __restrict__ val, float next_val,
-                                         float alive_f32, bool is_last, double alive_last, float g32, float gl32,
-                                         int64_t idx) {
-    Step s;
-    const float r = rew[idx], v = val[idx];
-    if (!is_last) {
-        const float t1 = __fmul_rn(g32, next_val);
-        const float t2 = __fmul_rn(t1, alive_f32);
-        const float t3 = __fadd_rn(r, t2);
-        s.delta = (double)__fsub_rn(t3, v);
-        s.coef = (double)__fmul_rn(gl32, alive_f32);
-    } else {
-        // next_non_terminal comes from a bool array -> float64 from here on
-        const double t2 = __dmul_rn((double)__fmul_rn(g32, next_val), alive_last);
-        s.delta = __dsub_rn(__dadd_rn((double)r, t2), (double)v);
-        s.coef = 0.0;   // multiplies the initial carry 0
-    }
-    return s;
-}
+constexpr int BS = 8;   // steps per thread
 
-constexpr int UB = 8;   // time steps whose loads are batched
+struct Map2 { double Mr, Br, Mc, Bc; };     // affine maps of the two signals
 
-// both signals' (delta, coef) at time t for column col
-__device__ __forceinline__ void load_steps(const GaeArgs& a, int t, int col, float lvr, float lvc, double alive_last,
-                                           Step& sr, Step& sc) {
-    const int64_t idx = (int64_t)t * a.E + col;
-    const bool last = (t == a.T - 1);
-    const float alive = last ? 0.f : __fsub_rn(1.0f, a.dones[idx + a.E]);
-    const float nvr = last ? lvr : a.vr[idx + a.E];
-    const float nvc = last ? lvc : a.vc[idx + a.E];
-    sr = gae_step(a.r, a.vr, nvr, alive, last, alive_last, a.g_r, a.gl_r, idx);
-    sc = gae_step(a.c, a.vc, nvc, alive, last, alive_last, a.g_c, a.gl_c, idx);
-}
+__device__ __forceinline__ double shfl_up_d(double v, int delta) { return __shfl_up_sync(0xffffffffu, v, delta); }
 
-// CG = env columns per CTA (32: a warp row is one 128-byte segment; 8: four time sub-chunks share a warp, each lane group
-// reading a 32-byte sector -- 4x more chunks and 4x more CTAs for narrow / mid-sized buffers).  NW warps; the time axis is
-// split into NCH = NW * (32 / CG) chunks.
-template <int NW, int CG>
-__global__ void __launch_bounds__(NW * 32) dual_gae_kernel(const GaeArgs a) {
-    constexpr int SUB = 32 / CG, NCH = NW * SUB;
-    __shared__ double sM[2][NCH][CG], sB[2][NCH][CG];
+// NT threads, CG adjacent env columns per CTA; a window = (NT / CG) blocks of BS steps.
+template <int NT, int CG>
+__global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dual_gae_kernel(const GaeArgs a) {
+    constexpr int LG = 32 / CG, NW = NT / 32, SLOTS = NW * LG;
+    __shared__ double sAgg[NW][CG][4];
+    __shared__ double sCarry[2][CG][2];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int cl = lane % CG;                       // column within the CTA's group
-    const int ch = w * SUB + lane / CG;             // this thread's time chunk
+    const int cl = lane % CG, lg = lane / CG;        // column within the group, time slot within the warp
+    const int slot = w * LG + lg;                    // slot 0 = the LATEST block of a window
     const int col = blockIdx.x * CG + cl;
-    const bool active = col < a.E;
+    const bool active_col = col < a.E;
     const int T = a.T, E = a.E;
-    const int Lc = (T + NCH - 1) / NCH;
-    const int lo = min(T, ch * Lc), hi = min(T, lo + Lc);
+    const int nb = (T + BS - 1) / BS, nwin = (nb + SLOTS - 1) / SLOTS;
 
     double alive_last = 0.0;
     float lvr = 0.f, lvc = 0.f;
-    if (active) {
+    if (active_col) {
         alive_last = a.last_dones[col] ? 0.0 : 1.0;
         lvr = a.last_vr[col];
         lvc = a.last_vc[col];
     }
+    if (threadIdx.x < CG * 2) sCarry[0][threadIdx.x >> 1][threadIdx.x & 1] = 0.0;   // A_T = 0
+    __syncthreads();
 
-    // ---- phase 1: fold the chunk.  Loads of UB consecutive steps are issued together (the recurrence itself is
-    // serial, the memory traffic must not be), then folded in order.
-    double Mr = 1.0, Br = 0.0, Mc = 1.0, Bc = 0.0;
-    if (active) {
-        for (int t1 = hi - 1; t1 >= lo; t1 -= UB) {
-            Step sr[UB], sc[UB];
+    for (int k = 0; k < nwin; ++k) {
+        const int tb = nb - 1 - k * SLOTS - slot;
+        const bool act = active_col && tb >= 0;
+        const int t0 = tb * BS;
+        // ---- raw inputs of the block, all loads independent.  vr / vc carry one extra row (the next state's value), al[u] is
+        // next_non_terminal after step t0 + u (float32 path); the step that ends the buffer uses the float64 path below.
+        float r[BS], c[BS], vr[BS + 1], vc[BS + 1], al[BS];
+        if (act) {
 #pragma unroll
-            for (int u = 0; u < UB; ++u) {
-                const int t = t1 - u;
-                if (t >= lo) load_steps(a, t, col, lvr, lvc, alive_last, sr[u], sc[u]);
+            for (int u = 0; u <= BS; ++u) {
+                const int t = t0 + u;
+                const int64_t idx = (int64_t)t * E + col;
+                const bool in = t < T;
+                vr[u] = in ? a.vr[idx] : lvr;
+                vc[u] = in ? a.vc[idx] : lvc;
+                if (u < BS) { r[u] = in ? a.r[idx] : 0.f; c[u] = in ? a.c[idx] : 0.f; }
+                if (u > 0) al[u - 1] = in ? __fsub_rn(1.0f, a.dones[idx]) : 0.f;
             }
+        }
+        // (delta, coef) of step u exactly as numpy evaluates buffers.py:528-537
+        auto step = [&](int u, float rew, float val, float nval, float g32, float gl32) {
+            Step s;
+            if (t0 + u != T - 1) {
+                const float t1 = __fmul_rn(g32, nval);
+                const float t2 = __fmul_rn(t1, al[u]);
+                const float t3 = __fadd_rn(rew, t2);
+                s.delta = (double)__fsub_rn(t3, val);
+                s.coef = (double)__fmul_rn(gl32, al[u]);
+            } else {       // next_non_terminal comes from a bool array -> float64 from here on
+                const double t2 = __dmul_rn((double)__fmul_rn(g32, nval), alive_last);
+                s.delta = __dsub_rn(__dadd_rn((double)rew, t2), (double)val);
+                s.coef = 0.0;   // multiplies the initial carry 0
+            }
+            return s;
+        };
+        // ---- fold the block into one affine map per signal
+        Map2 m = {1.0, 0.0, 1.0, 0.0};
+        if (act) {
 #pragma unroll
-            for (int u = 0; u < UB; ++u) {
-                if (t1 - u >= lo) {
-                    Br = sr[u].delta + sr[u].coef * Br;
-                    Mr = sr[u].coef * Mr;
-                    Bc = sc[u].delta + sc[u].coef * Bc;
-                    Mc = sc[u].coef * Mc;
+            for (int u = BS - 1; u >= 0; --u) {
+                if (t0 + u < T) {
+                    const Step sr = step(u, r[u], vr[u], vr[u + 1], a.g_r, a.gl_r);
+                    const Step sc = step(u, c[u], vc[u], vc[u + 1], a.g_c, a.gl_c);
+                    m.Br = sr.delta + sr.coef * m.Br; m.Mr = sr.coef * m.Mr;
+                    m.Bc = sc.delta + sc.coef * m.Bc; m.Mc = sc.coef * m.Mc;
                 }
             }
         }
-    }
-    sM[0][ch][cl] = Mr; sB[0][ch][cl] = Br;
-    sM[1][ch][cl] = Mc; sB[1][ch][cl] = Bc;
-    __syncthreads();
-
-    // ---- phase 2: carry-in of this chunk = composition of all later chunks applied to A_T = 0
-    double carry_r = 0.0, carry_c = 0.0;
-    for (int cc = NCH - 1; cc > ch; --cc) {
-        carry_r = sB[0][cc][cl] + sM[0][cc][cl] * carry_r;
-        carry_c = sB[1][cc][cl] + sM[1][cc][cl] * carry_c;
-    }
-
-    // ---- phase 3: replay with the reference's rounding, store
-    if (!active) return;
-    for (int t1 = hi - 1; t1 >= lo; t1 -= UB) {
-        Step sr[UB], sc[UB];
-        float vr[UB], vc[UB];
+        // ---- inclusive scan over the warp's time slots (slot order: later blocks first).  mine o theirs.
+        Map2 inc = m;
 #pragma unroll
-        for (int u = 0; u < UB; ++u) {
-            const int t = t1 - u;
-            if (t >= lo) {
-                load_steps(a, t, col, lvr, lvc, alive_last, sr[u], sc[u]);
-                vr[u] = a.vr[(int64_t)t * E + col];
-                vc[u] = a.vc[(int64_t)t * E + col];
+        for (int off = 1; off < LG; off <<= 1) {
+            const double pMr = shfl_up_d(inc.Mr, off * CG), pBr = shfl_up_d(inc.Br, off * CG);
+            const double pMc = shfl_up_d(inc.Mc, off * CG), pBc = shfl_up_d(inc.Bc, off * CG);
+            if (lg >= off) {
+                inc.Br = inc.Br + inc.Mr * pBr; inc.Mr = inc.Mr * pMr;
+                inc.Bc = inc.Bc + inc.Mc * pBc; inc.Mc = inc.Mc * pMc;
             }
         }
+        Map2 exc;       // composition of the warp's earlier slots (identity for the first)
+        exc.Mr = shfl_up_d(inc.Mr, CG); exc.Br = shfl_up_d(inc.Br, CG);
+        exc.Mc = shfl_up_d(inc.Mc, CG); exc.Bc = shfl_up_d(inc.Bc, CG);
+        if (lg == 0) exc = Map2{1.0, 0.0, 1.0, 0.0};
+        if (lg == LG - 1) { sAgg[w][cl][0] = inc.Mr; sAgg[w][cl][1] = inc.Br; sAgg[w][cl][2] = inc.Mc; sAgg[w][cl][3] = inc.Bc; }
+        __syncthreads();
+        // ---- carry into this warp: the window's carry pushed through the earlier warps' aggregates
+        double xr = sCarry[k & 1][cl][0], xc = sCarry[k & 1][cl][1];
+        for (int ww = 0; ww < w; ++ww) {
+            xr = sAgg[ww][cl][1] + sAgg[ww][cl][0] * xr;
+            xc = sAgg[ww][cl][3] + sAgg[ww][cl][2] * xc;
+        }
+        if (w == NW - 1 && lg == LG - 1) {        // the window's carry-out (into the next, earlier window)
+            sCarry[(k + 1) & 1][cl][0] = inc.Br + inc.Mr * xr;
+            sCarry[(k + 1) & 1][cl][1] = inc.Bc + inc.Mc * xc;
+        }
+        double carry_r = exc.Br + exc.Mr * xr, carry_c = exc.Bc + exc.Mc * xc;
+        // ---- replay from registers with the reference's rounding, store
+        if (act) {
 #pragma unroll
-        for (int u = 0; u < UB; ++u) {
-            const int t = t1 - u;
-            if (t >= lo) {
-                const int64_t idx = (int64_t)t * E + col;
-                carry_r = __dadd_rn(sr[u].delta, __dmul_rn(sr[u].coef, carry_r));
-                carry_c = __dadd_rn(sc[u].delta, __dmul_rn(sc[u].coef, carry_c));
-                const float ar = (float)carry_r, ac = (float)carry_c;
-                a.adv_r[idx] = ar;
-                a.adv_c[idx] = ac;
-                a.ret_r[idx] = __fadd_rn(ar, vr[u]);
-                a.ret_c[idx] = __fadd_rn(ac, vc[u]);
+            for (int u = BS - 1; u >= 0; --u) {
+                if (t0 + u < T) {
+                    const int64_t idx = (int64_t)(t0 + u) * E + col;
+                    const Step sr = step(u, r[u], vr[u], vr[u + 1], a.g_r, a.gl_r);
+                    const Step sc = step(u, c[u], vc[u], vc[u + 1], a.g_c, a.gl_c);
+                    carry_r = __dadd_rn(sr.delta, __dmul_rn(sr.coef, carry_r));
+                    carry_c = __dadd_rn(sc.delta, __dmul_rn(sc.coef, carry_c));
+                    const float ar = (float)carry_r, ac = (float)carry_c;
+                    a.adv_r[idx] = ar;
+                    a.adv_c[idx] = ac;
+                    a.ret_r[idx] = __fadd_rn(ar, vr[u]);
+                    a.ret_c[idx] = __fadd_rn(ac, vc[u]);
+                }
             }
         }
+        __syncthreads();   // the next window's carry is in place; sAgg may be rewritten
     }
 }
 
 int dual_gae_device(const GaeArgs& a, cudaStream_t st) {
     if (a.T <= 0 || a.E <= 0) return 0;
-    // Few columns: narrow column groups (8 per CTA) and many time chunks, so that short buffers still spread over
-    // many threads / CTAs (the reference's 2048 x 5 buffer is ONE CTA with 64 chunks of 32 steps).  Many columns:
-    // 32-column groups (full 128-byte rows), the grid alone fills the GPU.
-    const int g8 = (a.E + 7) / 8, g32 = (a.E + 31) / 32;
-    if (g32 >= 4 * sm_count()) {
-        if (a.T >= 256) dual_gae_kernel<8, 32><<<g32, 8 * 32, 0, st>>>(a);
-        else dual_gae_kernel<1, 32><<<g32, 32, 0, st>>>(a);
-    } else if (a.T >= 1024) {
-        dual_gae_kernel<16, 8><<<g8, 16 * 32, 0, st>>>(a);
-    } else if (a.T >= 128) {
-        dual_gae_kernel<4, 8><<<g8, 4 * 32, 0, st>>>(a);
-    } else {
-        dual_gae_kernel<1, 8><<<g8, 32, 0, st>>>(a);
-    }
+    // wide buffers: 8-column groups (full 32-byte sectors), 256-step windows, two CTAs per SM; narrow ones (the reference's
+    // 2048 x 5 rollout): 4-column groups and 1024-step windows so that few CTAs still cover the time axis quickly
+    if (a.E >= 64) dual_gae_kernel<256, 8><<<(a.E + 7) / 8, 256, 0, st>>>(a);
+    else dual_gae_kernel<512, 4><<<(a.E + 3) / 4, 512, 0, st>>>(a);
     ICRL_LAUNCH_CHECK();
     return 0;
 }
