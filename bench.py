@@ -528,6 +528,21 @@ def family_rooflines(learner, peaks):
                                                         0.99, 1e-8, 10.0, 1, 1, _lib.ptr(state), _lib.ptr(outs[0]),
                                                         _lib.current_stream())))
     out["k5_rollout"] = {"rows": n, "us": d * 1e6, "GB/s": 13 * n / d / 1e9, "frac_hbm": 13 * n / d / 1e9 / peak}
+    # the reference's DEFAULT cost path: one ConstraintNet.cost_function([n_envs, obs], [n_envs, act]) host call per environment
+    # step (VecCostWrapper.step_wait, vec_cost_wrapper.py:62) -- H2D + K1 + D2H + sync every call; wall clock, host buffers
+    ho = np.random.default_rng(0).standard_normal((E, w.obs_dim))
+    ha = (np.random.default_rng(1).integers(0, w.act_dim, size=(E,)).astype(np.float32) if w.is_discrete
+          else np.random.default_rng(1).standard_normal((E, w.act_dim)).astype(np.float32))
+    for _ in range(20):
+        learner.cn.cost_function(ho, ha)
+    t0 = time.perf_counter()
+    for _ in range(300):
+        learner.cn.cost_function(ho, ha)
+    per_call = (time.perf_counter() - t0) / 300
+    out["k1_per_env_step_call"] = {"rows": E, "us_per_call_wall": per_call * 1e6,
+                                   "us_per_rollout_wall": per_call * 1e6 * T,
+                                   "note": "per-step mode (the drivers' default); the whole-buffer relabel (K1 + K5 once per "
+                                           "rollout, ICRL_WHOLE_BUFFER_RELABEL=1) is what `value` / `e2e` time"}
     return out
 
 
