@@ -14,6 +14,8 @@
 //     returns = adv_f32 + value_f32.
 // Reward and cost scans run in the same thread (two independent dependency chains).  CG adjacent columns per CTA: 8 (every
 // row access of a lane group is one full 32-byte sector) for wide buffers, 4 for narrow ones (twice the time slots per CTA).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace icrl {
@@ -39,7 +41,7 @@ __device__ __forceinline__ double shfl_up_d(double v, int delta) { return __shfl
 
 // NT threads, CG adjacent env columns per CTA; a window = (NT / CG) blocks of BS steps.
 template <int NT, int CG>
-__global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) dual_gae_kernel(const GaeArgs a) {
+__global__ void __launch_bounds__(NT, NT <= 128 ? 4 : NT <= 256 ? 2 : 1) dual_gae_kernel(const GaeArgs a) {
     constexpr int LG = 32 / CG, NW = NT / 32, SLOTS = NW * LG;
     __shared__ double sAgg[NW][CG][4];
     __shared__ double sCarry[2][CG][2];
@@ -163,7 +165,9 @@ int dual_gae_device(const GaeArgs& a, cudaStream_t st) {
     if (a.T <= 0 || a.E <= 0) return 0;
     // wide buffers: 8-column groups (full 32-byte sectors), 256-step windows, two CTAs per SM; narrow ones (the reference's
     // 2048 x 5 rollout): 4-column groups and 1024-step windows so that few CTAs still cover the time axis quickly
-    if (a.E >= 64) dual_gae_kernel<256, 8><<<(a.E + 7) / 8, 256, 0, st>>>(a);
+    static const int forced_nt = getenv("ICRL_K3_NT") ? atoi(getenv("ICRL_K3_NT")) : 0;     // A/B switch (profiling)
+    if (a.E >= 64 && forced_nt == 128) dual_gae_kernel<128, 8><<<(a.E + 7) / 8, 128, 0, st>>>(a);
+    else if (a.E >= 64) dual_gae_kernel<256, 8><<<(a.E + 7) / 8, 256, 0, st>>>(a);
     else dual_gae_kernel<512, 4><<<(a.E + 3) / 4, 512, 0, st>>>(a);
     ICRL_LAUNCH_CHECK();
     return 0;

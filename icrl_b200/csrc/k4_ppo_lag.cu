@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
     bool kl_stopped = false;
     double epoch_kl_sum = 0.0;
     bool stop_all = false;
-    const bool timed = (a.timing != nullptr) && tid == 0 && working;
+    const bool timed = (a.timing != nullptr) && tid == 0 && working && cluster_id == 0;
     long long tmark = clock64();
     unsigned long long tacc[16];
 #pragma unroll
@@ -1657,6 +1657,8 @@ int64_t icrl_ppo_param_count(const icrl_ppo_cfg* cfg) {
     return icrl::ppo_fill_offsets(a);
 }
 
+static void ppo_print_timing(unsigned long long* timing_dev, cudaStream_t st, double steps);
+
 static int ppo_train_impl(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* params, float* adam_m, float* adam_v,
                           int64_t adam_step_before, float* step_stats, int32_t* result, const icrl_ppo_dist* dist,
                           void* stream) {
@@ -1702,6 +1704,11 @@ static int ppo_train_impl(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, fl
         icrl::set_error("obs_dim %d too large for the PPO kernel (max 128)", a.D);
         return ICRL_EUNSUPPORTED;
     }
+    static unsigned long long* timing_dev = nullptr;
+    const bool want_timing = getenv("ICRL_PPO_TIMING") != nullptr;
+    if (want_timing && !timing_dev) cudaMalloc(&timing_dev, 128 * sizeof(unsigned long long));
+    a.timing = want_timing ? timing_dev : nullptr;
+    auto print_timing = [&](double steps) { ppo_print_timing(timing_dev, st, steps); };
     // large batches run on many clusters (ICRL_PPO_WIDE=0/1 forces the choice, ICRL_PPO_WIDE_CLUSTERS caps the cluster count)
     bool wide = a.B >= icrl::WIDE_MIN_BATCH;
     if (const char* m = getenv("ICRL_PPO_WIDE")) wide = atoi(m) != 0;
@@ -1736,10 +1743,16 @@ static int ppo_train_impl(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, fl
         if ((rc = icrl::device_scratch(icrl::SLOT_PPO2, (size_t)n_alloc * a.AP * 4, &as))) return rc;
         if ((rc = icrl::device_scratch(icrl::SLOT_PPO3, (size_t)n_alloc * 8 * 4, &ss))) return rc;
         if (wide) {
-            if (nt1 <= 1) return icrl::launch_ppo_wide<1>(a, st, n_clusters, (float*)xs, (float*)as, (float*)ss, (float*)advstats);
-            if (nt1 <= 2) return icrl::launch_ppo_wide<2>(a, st, n_clusters, (float*)xs, (float*)as, (float*)ss, (float*)advstats);
-            if (nt1 <= 4) return icrl::launch_ppo_wide<4>(a, st, n_clusters, (float*)xs, (float*)as, (float*)ss, (float*)advstats);
-            return icrl::launch_ppo_wide<8>(a, st, n_clusters, (float*)xs, (float*)as, (float*)ss, (float*)advstats);
+            if (nt1 <= 1) rc = icrl::launch_ppo_wide<1>(a, st, n_clusters, (float*)xs, (float*)as, (float*)ss, (float*)advstats);
+            else if (nt1 <= 2) rc = icrl::launch_ppo_wide<2>(a, st, n_clusters, (float*)xs, (float*)as, (float*)ss, (float*)advstats);
+            else if (nt1 <= 4) rc = icrl::launch_ppo_wide<4>(a, st, n_clusters, (float*)xs, (float*)as, (float*)ss, (float*)advstats);
+            else rc = icrl::launch_ppo_wide<8>(a, st, n_clusters, (float*)xs, (float*)as, (float*)ss, (float*)advstats);
+            if (rc == 0 && want_timing) {       // the last epoch's launch; per step of that launch
+                fprintf(stderr, "[ppo timing] many-cluster kernel, %d clusters, last epoch (%d steps of %d rows):\n", n_clusters,
+                        a.steps_per_epoch, a.B);
+                print_timing((double)a.steps_per_epoch);
+            }
+            return rc;
         }
         const long long blocks = (n_alloc + 7) / 8;
         const int grid = (int)(blocks < 8LL * icrl::sm_count() ? blocks : 8LL * icrl::sm_count());
@@ -1751,21 +1764,22 @@ static int ppo_train_impl(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, fl
         a.xs = (const float*)xs; a.as = (const float*)as; a.ss = (const float*)ss;
         a.advstats = (const float*)advstats;
     }
-    static unsigned long long* timing_dev = nullptr;
-    const bool want_timing = getenv("ICRL_PPO_TIMING") != nullptr;
-    if (want_timing && !timing_dev) cudaMalloc(&timing_dev, 128 * sizeof(unsigned long long));
-    a.timing = want_timing ? timing_dev : nullptr;
     if (nt1 <= 1) rc = icrl::launch_ppo<1>(a, st);
     else if (nt1 <= 2) rc = icrl::launch_ppo<2>(a, st);
     else if (nt1 <= 4) rc = icrl::launch_ppo<4>(a, st);
     else rc = icrl::launch_ppo<8>(a, st);
-    if (rc == 0 && want_timing) {   // profiling aid: per-phase cycles of thread 0 of each trunk CTA (synchronises!)
+    if (rc == 0 && want_timing) print_timing((double)(a.max_steps > 0 ? a.max_steps : a.n_epochs * a.steps_per_epoch));
+    return rc;
+}
+
+// profiling aid (ICRL_PPO_TIMING=1): per-phase cycles of thread 0 of each trunk's first CTA (cluster 0); synchronises!
+static void ppo_print_timing(unsigned long long* timing_dev, cudaStream_t st, double steps) {
+    {
         unsigned long long h[128];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, timing_dev, sizeof(h), cudaMemcpyDeviceToHost);
         const char* names[11] = {"wait+sync", "prefetch", "L1", "L2", "head", "headgrad+dH2", "dW2+dH1", "dW1", "reduce+stats",
                                  "xchg+cluster", "adam"};
-        const double steps = (double)(a.max_steps > 0 ? a.max_steps : a.n_epochs * a.steps_per_epoch);
         for (int r = 0; r < icrl::NCTA; r += (r == 0 ? 1 : 2)) {
             fprintf(stderr, "[ppo timing] cta %d cycles/step:", r);
             double tot = 0;
@@ -1774,7 +1788,6 @@ static int ppo_train_impl(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, fl
                     h[r * 16 + 11] / steps, h[r * 16 + 12] / steps, h[r * 16 + 13] / steps, h[r * 16 + 14] / steps, h[r * 16 + 15] / steps);
         }
     }
-    return rc;
 }
 
 int icrl_ppo_train(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, float* params, float* adam_m, float* adam_v,
