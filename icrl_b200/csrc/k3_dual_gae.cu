@@ -163,12 +163,17 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? 4 : NT <= 256 ? 2 : 1) dual_ga
 
 int dual_gae_device(const GaeArgs& a, cudaStream_t st) {
     if (a.T <= 0 || a.E <= 0) return 0;
-    // wide buffers: 8-column groups (full 32-byte sectors), 256-step windows, two CTAs per SM; narrow ones (the reference's
-    // 2048 x 5 rollout): 4-column groups and 1024-step windows so that few CTAs still cover the time axis quickly
-    static const int forced_nt = getenv("ICRL_K3_NT") ? atoi(getenv("ICRL_K3_NT")) : 0;     // A/B switch (profiling)
-    if (a.E >= 64 && forced_nt == 128) dual_gae_kernel<128, 8><<<(a.E + 7) / 8, 128, 0, st>>>(a);
-    else if (a.E >= 64) dual_gae_kernel<256, 8><<<(a.E + 7) / 8, 256, 0, st>>>(a);
-    else dual_gae_kernel<512, 4><<<(a.E + 3) / 4, 512, 0, st>>>(a);
+    // launch shape by column count (measured, profiles/SUMMARY_r02.md): the reference's 2048 x 5 rollout: 4-column groups and
+    // 1024-step windows so that two CTAs cover the time axis quickly; < 1024 columns: 4-column groups (twice the CTAs);
+    // wide buffers: 8-column groups (a lane group's row access is one full 32-byte sector), 256-step windows, two CTAs per SM,
+    // and from 4096 columns on 128-thread CTAs, four per SM (load and replay phases of different CTAs overlap better)
+    static const int forced_nt = getenv("ICRL_K3_NT") ? atoi(getenv("ICRL_K3_NT")) : 0;     // A/B switches (profiling)
+    static const int forced_cg = getenv("ICRL_K3_CG") ? atoi(getenv("ICRL_K3_CG")) : 0;
+    const bool many_cols = a.E >= 4096;      // enough column groups to fill every SM four times with small CTAs
+    if (a.E < 64) dual_gae_kernel<512, 4><<<(a.E + 3) / 4, 512, 0, st>>>(a);
+    else if (forced_cg == 4 || (forced_cg == 0 && a.E < 1024)) dual_gae_kernel<256, 4><<<(a.E + 3) / 4, 256, 0, st>>>(a);
+    else if (forced_nt == 128 || (forced_nt == 0 && many_cols)) dual_gae_kernel<128, 8><<<(a.E + 7) / 8, 128, 0, st>>>(a);
+    else dual_gae_kernel<256, 8><<<(a.E + 7) / 8, 256, 0, st>>>(a);
     ICRL_LAUNCH_CHECK();
     return 0;
 }

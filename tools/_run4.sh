@@ -1,8 +1,5 @@
 set -u
-mkdir -p gpurun_out
-echo "== K3 variants"; python tools/kernel_times.py k3 4194304 16777216; ICRL_K3_NT=128 python tools/kernel_times.py k3 4194304 16777216
-echo "== K4 wide timing"
-ICRL_PPO_TIMING=1 python tools/k4_wide_time.py antwall 1048576 2>&1 | tail -8
-ICRL_PPO_TIMING=1 python tools/k4_wide_time.py halfcheetah 1048576 2>&1 | tail -8
-echo "== single cluster timing (Ant, HC)"
-ICRL_PPO_TIMING=1 python tools/k4_wide_time.py antwall 10240 128 2 2>&1 | tail -5
+python tools/kernel_times.py k3 1048576 4194304 16777216
+echo "== CG=4"; ICRL_K3_CG=4 python tools/kernel_times.py k3 1048576 4194304 16777216
+echo "== NT=256"; ICRL_K3_NT=256 python tools/kernel_times.py k3 16777216
+python -m pytest tests/test_k3_gpu.py -q -m gpu 2>&1 | tail -2
