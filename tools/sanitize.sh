@@ -9,11 +9,11 @@ OUT=gpurun_out
 mkdir -p $OUT
 : > $OUT/sanitize_$R.summary
 for tool in memcheck racecheck synccheck; do
-    timeout 1200 compute-sanitizer --tool $tool --print-limit 30 python __graft_entry__.py smoke > $OUT/sanitize_${tool}_$R.log 2>&1
+    timeout 420 compute-sanitizer --tool $tool --print-limit 30 python __graft_entry__.py smoke > $OUT/sanitize_${tool}_$R.log 2>&1
     echo "== $tool (single-cluster K4): exit $?" >> $OUT/sanitize_$R.summary
     grep -E "ERROR SUMMARY|RACECHECK SUMMARY|smoke ok|Error|error" $OUT/sanitize_${tool}_$R.log | tail -6 >> $OUT/sanitize_$R.summary
 done
-ICRL_PPO_WIDE=1 ICRL_PPO_WIDE_CLUSTERS=6 timeout 1200 compute-sanitizer --tool memcheck --print-limit 30 \
+ICRL_PPO_WIDE=1 ICRL_PPO_WIDE_CLUSTERS=6 timeout 420 compute-sanitizer --tool memcheck --print-limit 30 \
     python __graft_entry__.py smoke > $OUT/sanitize_memcheck_wide_$R.log 2>&1
 echo "== memcheck (many-cluster K4 forced, 6 clusters): exit $?" >> $OUT/sanitize_$R.summary
 grep -E "ERROR SUMMARY|smoke ok|Error|error" $OUT/sanitize_memcheck_wide_$R.log | tail -6 >> $OUT/sanitize_$R.summary
