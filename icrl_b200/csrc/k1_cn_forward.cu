@@ -100,6 +100,234 @@ __global__ void __launch_bounds__(128) cn_forward_kernel(const __grid_constant__
     }
 }
 
+// ---------------------------------------------------------------- packed-FP32 kernel (the default)
+// Measured on B200 (tools/micro/ffma2_bench.cu, profiles/ffma2_bench_r02.txt): the thread-per-row loop above is bound by the
+// RETURN BANDWIDTH OF BROADCAST LDS.128 (one weight quad per ~2.2 cycles per SM: every weight is fetched once per row) and
+// by 3-register FFMA issue, at 45 % of the FP32 peak whatever the FMA flavour.  Here a thread owns 2 RP rows and keeps them as
+// the two halves of 64-bit registers: one `fma.rn.f32x2` (SASS FFMA2, the weight as a broadcast scalar operand) updates one
+// hidden unit of a row PAIR, so every weight read from shared memory feeds 2 RP rows and the FMA instruction count halves.
+// Per input k and row pair: HP FFMA2 + HP/4 LDS.128 (shared by all RP pairs) + the two inputs.  The arithmetic per row is
+// the same IEEE fma sequence as before (bias + sum over k in order): results are bit-identical to the scalar kernel.
+// Tiles of 2 RP blockDim rows are staged by TMA bulk copies, double buffered when shared memory allows (the next tile's
+// copy is in flight while this one is computed).  Hidden activations of layers >= 1 pass through thread-private shared
+// memory slots only to avoid dynamic register indexing (no barrier involved).
+__device__ __forceinline__ void ffma2_bcast(float2& acc, const float2 x, const float w) {
+    unsigned long long a, xx, ww;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(acc.x), "f"(acc.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(xx) : "f"(x.x), "f"(x.y));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));                   // folded into the FFMA2 operand by ptxas
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(xx), "l"(ww));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(a));
+}
+
+struct CnPairSmem {
+    int bar, mean, rstd, low, high, w[ICRL_MAX_HIDDEN], b[ICRL_MAX_HIDDEN], wout, stage, stage_bytes, acs_off, h, total;
+};
+__host__ __device__ inline CnPairSmem cn_pair_layout(const CnPlan& p, int HP, int NT, int RP, int obs_elem, int nbuf) {
+    CnPairSmem s;
+    const int TILE = 2 * RP * NT;
+    int off = 0;
+    s.bar = off; off += 16;
+    s.mean = off; off += p.has_norm ? p.obs_dim * 8 : 0;
+    s.rstd = off; off += p.has_norm ? p.obs_dim * 8 : 0;
+    s.low = off; off += p.has_clip_acs ? p.acs_dim * 4 : 0;
+    s.high = off; off += p.has_clip_acs ? p.acs_dim * 4 : 0;
+    off = align_up(off, 16);
+    for (int l = 0; l < ICRL_MAX_HIDDEN; ++l) {
+        s.w[l] = off;
+        if (l < p.n_hidden) off += (l == 0 ? align_up(p.n_select, 8) : HP) * HP * 4;
+        s.b[l] = off;
+        if (l < p.n_hidden) off += HP * 4;
+    }
+    s.wout = off; off += (HP + 4) * 4;
+    off = align_up(off, 16);
+    s.acs_off = align_up(TILE * p.obs_dim * obs_elem, 16);
+    s.stage_bytes = s.acs_off + align_up(TILE * p.acs_w * 4, 16);
+    s.stage = off; off += nbuf * s.stage_bytes;
+    s.h = off; off += (p.n_hidden > 1) ? RP * HP * NT * 8 : 0;
+    s.total = off;
+    return s;
+}
+
+template <typename ObsT, int HP, int RP>
+__global__ void __launch_bounds__(128) cn_forward_pair_kernel(const __grid_constant__ CnPlan plan, const ObsT* __restrict__ obs,
+                                                              const float* __restrict__ acs, int64_t n_rows,
+                                                              float* __restrict__ out, int out_kind, int tma_ok, int nbuf) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int NT = blockDim.x, TILE = 2 * RP * NT, tid = threadIdx.x;
+    const CnPairSmem L = cn_pair_layout(plan, HP, NT, RP, sizeof(ObsT), nbuf);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
+    CnSmem V;                      // the common helpers' view: weights + the current staging buffer
+    V.bar = L.bar; V.mean = L.mean; V.rstd = L.rstd; V.low = L.low; V.high = L.high; V.wout = L.wout;
+    for (int l = 0; l < ICRL_MAX_HIDDEN; ++l) { V.w[l] = L.w[l]; V.b[l] = L.b[l]; }
+    V.obs = L.stage; V.acs = L.stage + L.acs_off; V.h = L.h; V.total = L.total;
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_mbar_init();
+    }
+    cn_load_weights<HP>(plan, V, smem);
+    __syncthreads();
+
+    bool fast_in = sizeof(ObsT) == 4 && !plan.has_norm && !plan.is_discrete && plan.n_select == plan.obs_dim + plan.acs_dim;
+    for (int k = 0; fast_in && k < plan.n_select; ++k) fast_in = plan.sel[k] == k;
+    const float co = (float)plan.clip_obs;
+
+    const int64_t n_tiles = (n_rows + TILE - 1) / TILE;
+    auto is_full = [&](int64_t tile) { return tile * TILE + TILE <= n_rows; };
+    auto issue = [&](int64_t tile, int buf) {          // one thread: both bulk copies of a FULL tile onto bar[buf]
+        const uint32_t ob = (uint32_t)TILE * plan.obs_dim * sizeof(ObsT), ab = (uint32_t)TILE * plan.acs_w * 4u;
+        unsigned char* base = smem + L.stage + buf * L.stage_bytes;
+        fence_proxy_async();
+        mbar_expect_tx(&bar[buf], ob + ab);
+        bulk_g2s(base, obs + tile * TILE * plan.obs_dim, ob, &bar[buf]);
+        bulk_g2s(base + L.acs_off, acs + tile * TILE * plan.acs_w, ab, &bar[buf]);
+    };
+    uint32_t phases = 0;
+    int it = 0;
+    if (nbuf == 2 && tma_ok && tid == 0 && blockIdx.x < n_tiles && is_full(blockIdx.x)) issue(blockIdx.x, 0);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = nbuf == 2 ? (it & 1) : 0;
+        const int64_t row0 = tile * TILE;
+        const int rows = (int)min((int64_t)TILE, n_rows - row0);
+        V.obs = L.stage + buf * L.stage_bytes;
+        V.acs = V.obs + L.acs_off;
+        if (nbuf == 2) {
+            const int64_t nxt = tile + gridDim.x;
+            if (tma_ok && tid == 0 && nxt < n_tiles && is_full(nxt)) issue(nxt, buf ^ 1);
+        }
+        if (tma_ok && rows == TILE) {
+            if (nbuf == 1 && tid == 0) issue(tile, 0);
+            mbar_wait(&bar[buf], (phases >> buf) & 1u);
+            phases ^= 1u << buf;
+        } else {
+            ObsT* so = reinterpret_cast<ObsT*>(smem + V.obs);
+            float* sa = reinterpret_cast<float*>(smem + V.acs);
+            const ObsT* go = obs + row0 * plan.obs_dim;
+            const float* ga = acs + row0 * plan.acs_w;
+            for (int i = tid; i < rows * plan.obs_dim; i += NT) so[i] = go[i];
+            for (int i = tid; i < rows * plan.acs_w; i += NT) sa[i] = ga[i];
+            __syncthreads();
+        }
+        // rows of this thread: pair p = (tid + 2p NT, tid + (2p + 1) NT).  Rows beyond `rows` read stale staging data; finite or
+        // not, it only reaches their own (discarded) outputs.
+        float2 acc[RP][HP];
+        {
+            const float* B = reinterpret_cast<const float*>(smem + V.b[0]);
+#pragma unroll
+            for (int j = 0; j < HP; ++j) {
+                const float b = B[j];
+#pragma unroll
+                for (int p = 0; p < RP; ++p) acc[p][j] = make_float2(b, b);
+            }
+            const float* W = reinterpret_cast<const float*>(smem + V.w[0]);
+            auto fma_row = [&](const float2 (&x)[RP], const float* wrow) {
+                const float4* w4 = reinterpret_cast<const float4*>(wrow);
+#pragma unroll
+                for (int j = 0; j < HP / 4; ++j) {
+                    const float4 w = w4[j];
+#pragma unroll
+                    for (int p = 0; p < RP; ++p) {
+                        ffma2_bcast(acc[p][4 * j + 0], x[p], w.x);
+                        ffma2_bcast(acc[p][4 * j + 1], x[p], w.y);
+                        ffma2_bcast(acc[p][4 * j + 2], x[p], w.z);
+                        ffma2_bcast(acc[p][4 * j + 3], x[p], w.w);
+                    }
+                }
+            };
+            if (fast_in) {
+                // every dimension selected in order, float32 observations, no normalisation, continuous actions (the
+                // HalfCheetah / Ant command lines): clip and go, no per-input indirection
+                const float* so = reinterpret_cast<const float*>(smem + V.obs);
+                const float* sa = reinterpret_cast<const float*>(smem + V.acs);
+                const float* lo = reinterpret_cast<const float*>(smem + V.low);
+                const float* hi = reinterpret_cast<const float*>(smem + V.high);
+#pragma unroll 2
+                for (int k = 0; k < plan.obs_dim; ++k) {
+                    float2 x[RP];
+#pragma unroll
+                    for (int p = 0; p < RP; ++p) {
+                        x[p].x = so[(tid + 2 * p * NT) * plan.obs_dim + k];
+                        x[p].y = so[(tid + (2 * p + 1) * NT) * plan.obs_dim + k];
+                        if (plan.has_clip_obs) {
+                            x[p].x = fminf(fmaxf(x[p].x, -co), co);
+                            x[p].y = fminf(fmaxf(x[p].y, -co), co);
+                        }
+                    }
+                    fma_row(x, W + k * HP);
+                }
+#pragma unroll 2
+                for (int k = 0; k < plan.acs_dim; ++k) {
+                    float2 x[RP];
+#pragma unroll
+                    for (int p = 0; p < RP; ++p) {
+                        x[p].x = sa[(tid + 2 * p * NT) * plan.acs_dim + k];
+                        x[p].y = sa[(tid + (2 * p + 1) * NT) * plan.acs_dim + k];
+                        if (plan.has_clip_acs) {
+                            x[p].x = fminf(fmaxf(x[p].x, lo[k]), hi[k]);
+                            x[p].y = fminf(fmaxf(x[p].y, lo[k]), hi[k]);
+                        }
+                    }
+                    fma_row(x, W + (plan.obs_dim + k) * HP);
+                }
+            } else {
+#pragma unroll 2
+                for (int k = 0; k < plan.n_select; ++k) {
+                    float2 x[RP];
+#pragma unroll
+                    for (int p = 0; p < RP; ++p) {
+                        x[p].x = cn_input<ObsT>(plan, V, smem, tid + 2 * p * NT, k);
+                        x[p].y = cn_input<ObsT>(plan, V, smem, tid + (2 * p + 1) * NT, k);
+                    }
+                    fma_row(x, W + k * HP);
+                }
+            }
+            float2* Hs = reinterpret_cast<float2*>(smem + L.h);
+            for (int l = 1; l < plan.n_hidden; ++l) {
+#pragma unroll
+                for (int j = 0; j < HP; ++j)
+#pragma unroll
+                    for (int p = 0; p < RP; ++p)
+                        Hs[(p * HP + j) * NT + tid] = make_float2(fmaxf(acc[p][j].x, 0.f), fmaxf(acc[p][j].y, 0.f));
+                const float* Bl = reinterpret_cast<const float*>(smem + V.b[l]);
+#pragma unroll
+                for (int j = 0; j < HP; ++j) {
+                    const float b = Bl[j];
+#pragma unroll
+                    for (int p = 0; p < RP; ++p) acc[p][j] = make_float2(b, b);
+                }
+                const float* Wl = reinterpret_cast<const float*>(smem + V.w[l]);
+                const int kin = plan.hidden[l - 1];
+#pragma unroll 2
+                for (int k = 0; k < kin; ++k) {
+                    float2 x[RP];
+#pragma unroll
+                    for (int p = 0; p < RP; ++p) x[p] = Hs[(p * HP + k) * NT + tid];
+                    fma_row(x, Wl + k * HP);
+                }
+            }
+        }
+        const float* WO = reinterpret_cast<const float*>(smem + V.wout);
+#pragma unroll
+        for (int p = 0; p < RP; ++p) {
+            float2 z = make_float2(WO[HP], WO[HP]);
+#pragma unroll
+            for (int j = 0; j < HP; ++j)
+                ffma2_bcast(z, make_float2(fmaxf(acc[p][j].x, 0.f), fmaxf(acc[p][j].y, 0.f)), WO[j]);
+            const int r0 = tid + 2 * p * NT, r1 = r0 + NT;
+            if (r0 < rows) {
+                const float pr = sigmoidf_ref(z.x);
+                out[row0 + r0] = out_kind == 0 ? 1.0f - pr : pr;
+            }
+            if (r1 < rows) {
+                const float pr = sigmoidf_ref(z.y);
+                out[row0 + r1] = out_kind == 0 ? 1.0f - pr : pr;
+            }
+        }
+        __syncthreads();   // everyone is done with this staging buffer before a later copy overwrites it
+    }
+}
+
 // Tensor-core variant (one or two hidden layers): a warp owns 32 rows of the 128-row tile (two m16 tiles) and runs every
 // layer as 3xTF32 mma.sync tiles.  Inputs are prepared once (select / normalise / clip in cn_input, thread = row so that
 // the per-input branches stay warp-uniform) into a padded shared-memory tile that feeds the A fragments.  Layer 1
@@ -276,6 +504,63 @@ __global__ void __launch_bounds__(128) cn_forward_mma_kernel(const __grid_consta
     }
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+template <typename ObsT, int HP, int RP>
+static int launch_pair_cfg(const CnPlan& plan, const void* obs, const float* acs, int64_t n_rows, float* out, int out_kind,
+                           cudaStream_t st, int nt, int nbuf) {
+    auto kern = cn_forward_pair_kernel<ObsT, HP, RP>;
+    const CnPairSmem L = cn_pair_layout(plan, HP, nt, RP, sizeof(ObsT), nbuf);
+    ICRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    int per_sm = 1;
+    ICRL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, L.total));
+    if (per_sm < 1) per_sm = 1;
+    const int tile = 2 * RP * nt;
+    const int64_t n_tiles = (n_rows + tile - 1) / tile;
+    const int grid = (int)((n_tiles < (int64_t)per_sm * sm_count()) ? n_tiles : (int64_t)per_sm * sm_count());
+    const int tma_ok = ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(acs)) & 15u) == 0 &&
+                       (tile * plan.obs_dim * sizeof(ObsT)) % 16 == 0 && (tile * plan.acs_w * 4) % 16 == 0;
+    kern<<<grid, nt, L.total, st>>>(plan, static_cast<const ObsT*>(obs), acs, n_rows, out, out_kind, tma_ok, nbuf);
+    ICRL_LAUNCH_CHECK();
+    return 0;
+}
+
+// Launch shape of the packed kernel: rows per thread (2 RP), threads per CTA and single / double buffering are chosen so
+// that (a) small buffers (a rollout) still spread over the SMs, (b) at least two CTAs fit an SM, double buffered if possible.
+template <typename ObsT, int HP>
+static int launch_forward_pair(const CnPlan& plan, const void* obs, const float* acs, int64_t n_rows, float* out,
+                               int out_kind, cudaStream_t st) {
+    static const int env_rp = env_int("ICRL_K1_RP", 0), env_nt = env_int("ICRL_K1_NT", 0), env_nbuf = env_int("ICRL_K1_NBUF", 0);
+    const int sms = sm_count();
+    int rp = 1;      // four rows per thread (RP 2) halves the weight reads again but measured slower: 260 us against 186 (HalfCheetah)
+    if (env_rp) rp = (env_rp >= 2 && HP <= 32) ? 2 : 1;
+    int nt = 128;
+    while (nt > 32 && (n_rows + 2 * rp * nt - 1) / (2 * rp * nt) < 2 * (int64_t)sms) nt /= 2;
+    const int budget = 113 * 1024;                   // two CTAs per SM
+    int nbuf = 2;
+    for (;;) {
+        if (cn_pair_layout(plan, HP, nt, rp, sizeof(ObsT), 2).total <= budget) { nbuf = 2; break; }
+        if (cn_pair_layout(plan, HP, nt, rp, sizeof(ObsT), 1).total <= budget) { nbuf = 1; break; }
+        if (nt > 32) { nt /= 2; continue; }
+        if (rp > 1) { rp = 1; continue; }
+        nbuf = 1;
+        break;
+    }
+    if (env_nt) nt = env_nt;
+    if (env_nbuf) nbuf = env_nbuf;
+    if (cn_pair_layout(plan, HP, nt, rp, sizeof(ObsT), nbuf).total > 227 * 1024) {
+        set_error("constraint net too large for shared memory (%d bytes)", cn_pair_layout(plan, HP, nt, rp, sizeof(ObsT), nbuf).total);
+        return ICRL_EUNSUPPORTED;
+    }
+    if constexpr (HP <= 32) {
+        if (rp == 2) return launch_pair_cfg<ObsT, HP, 2>(plan, obs, acs, n_rows, out, out_kind, st, nt, nbuf);
+    }
+    return launch_pair_cfg<ObsT, HP, 1>(plan, obs, acs, n_rows, out, out_kind, st, nt, nbuf);
+}
+
 template <typename ObsT, int HP>
 static int launch_forward(const CnPlan& plan, const void* obs, const float* acs, int64_t n_rows, float* out, int out_kind,
                           cudaStream_t st) {
@@ -310,6 +595,12 @@ static int launch_forward(const CnPlan& plan, const void* obs, const float* acs,
             return 0;
         }
     }
+    static const bool force_v1 = getenv("ICRL_K1_V1") != nullptr;             // the scalar thread-per-row kernel (A/B runs)
+    // packed kernel where it wins (measured on B200, 4.19 M rows: HalfCheetah 186 us against 203, PointCircle 324 against 516,
+    // LapGrid 59 against 60); the wide Ant net (HP 40, 484 B of staging per row) keeps the scalar kernel (2.25 ms against 2.62)
+    static const bool force_pair = getenv("ICRL_K1_PAIR") != nullptr;
+    if (!force_v1 && !force_ffma && (HP <= 32 || force_pair))
+        return launch_forward_pair<ObsT, HP>(plan, obs, acs, n_rows, out, out_kind, st);
     auto kern = cn_forward_kernel<ObsT, HP>;
     // pick the largest tile (== block size) whose shared memory fits
     int tile = 128;

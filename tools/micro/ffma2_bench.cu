@@ -89,6 +89,59 @@ __global__ void k_peak(float* out, int iters, long long* cyc) {
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+
+// register-only row loops: 24 hidden units, weights held in registers (no shared-memory traffic), NLDS extra broadcast
+// LDS.128 per 24 units mixed in (their results are consumed by a cheap xor so that they are not dead)
+template <int MODE, int NLDS>   // 0: FFMA acc[j] += x * w[j];  1: FFMA2 {acc_r0, acc_r1}[j] += {x_r0, x_r1} * w[j] (broadcast w);  2: FFMA2 {acc[j], acc[j+1]} += {x, x} * {w[j], w[j+1]}
+__global__ void k_reg(const float* __restrict__ wg, float* out, int iters, long long* cyc) {
+    __shared__ __align__(16) float S[64 * 4];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) S[i] = 0.f;
+    __syncthreads();
+    float w[24], acc[24];
+    float2 acc2[24];
+    for (int j = 0; j < 24; ++j) { w[j] = wg[j]; acc[j] = 0.f; acc2[j] = make_float2(0.f, 0.f); }
+    float x = 1.0f + 1e-6f * threadIdx.x;
+    float2 x2 = make_float2(x, x * 0.5f);
+    unsigned sink = 0;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int l = 0; l < NLDS; ++l) {
+            const uint4 v = *reinterpret_cast<const uint4*>(S + 4 * ((it + l) & 63));
+            sink ^= v.x ^ v.y ^ v.z ^ v.w;
+        }
+        if (MODE == 0) {
+#pragma unroll
+            for (int j = 0; j < 24; ++j) acc[j] = fmaf(x, w[j], acc[j]);
+        } else if (MODE == 1) {
+#pragma unroll
+            for (int j = 0; j < 24; ++j) {
+                unsigned long long a, xx, ww;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(acc2[j].x), "f"(acc2[j].y));
+                asm("mov.b64 %0, {%1, %2};" : "=l"(xx) : "f"(x2.x), "f"(x2.y));
+                asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w[j]));
+                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(xx), "l"(ww));
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(acc2[j].x), "=f"(acc2[j].y) : "l"(a));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                unsigned long long a, xx, ww;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(acc2[j].x), "f"(acc2[j].y));
+                asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(x));
+                asm("mov.b64 %0, {%1, %2};" : "=l"(ww) : "f"(w[2 * j]), "f"(w[2 * j + 1]));
+                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(xx), "l"(ww));
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(acc2[j].x), "=f"(acc2[j].y) : "l"(a));
+            }
+        }
+    }
+    const long long t1 = clock64();
+    float z = __uint_as_float(sink & 1u);
+    for (int j = 0; j < 24; ++j) z += acc[j] + acc2[j].x + acc2[j].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = z;
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
 int main() {
     float *out, *x, *w;
     long long* cyc;
@@ -109,6 +162,17 @@ int main() {
         printf("peak FFMA2 (3 x 64b) warps=%2d: %.1f FMA/cycle/SM\n", warps, 16.0 * 32 * warps * 4000 / h);
         k_peak<2><<<1, 32 * warps>>>(out, 4000, cyc); cudaDeviceSynchronize(); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
         printf("peak FFMA2 (bcast)   warps=%2d: %.1f FMA/cycle/SM\n", warps, 16.0 * 32 * warps * 4000 / h);
+    }
+
+    {
+        const int it2 = 4000;
+#define RUNREG(MODE, NLDS, FMAS, NAME)                                                                                      \
+    for (int warps : {8, 16, 32}) {                                                                                         \
+        k_reg<MODE, NLDS><<<1, 32 * warps>>>(w, out, it2, cyc); cudaDeviceSynchronize(); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost); \
+        printf("reg loop %-28s +%d LDS.128 warps=%2d: %.1f FMA/cycle/SM\n", NAME, NLDS, warps, (double)FMAS * 32 * warps * it2 / h);  \
+    }
+        RUNREG(0, 0, 24, "FFMA acc+=x*w[j]") RUNREG(1, 0, 48, "FFMA2 2 rows, bcast w[j]") RUNREG(2, 0, 24, "FFMA2 unit pairs, bcast x")
+        RUNREG(0, 3, 24, "FFMA acc+=x*w[j]") RUNREG(0, 6, 24, "FFMA acc+=x*w[j]") RUNREG(1, 3, 48, "FFMA2 2 rows, bcast w[j]") RUNREG(1, 6, 48, "FFMA2 2 rows, bcast w[j]") RUNREG(2, 6, 24, "FFMA2 unit pairs, bcast x")
     }
     printf("err=%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
