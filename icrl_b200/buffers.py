@@ -36,6 +36,7 @@ class RolloutBufferWithCost:
         self.action_dim = get_action_dim(action_space)
         self.device = device
         self._dev = None
+        self._stage = {}                # persistent pinned / device staging buffers of relabel_costs
         self.n_envs = n_envs
         self.reward_gamma, self.reward_gae_lambda = reward_gamma, reward_gae_lambda
         self.cost_gamma, self.cost_gae_lambda = cost_gamma, cost_gae_lambda
@@ -110,34 +111,61 @@ class RolloutBufferWithCost:
         T, E = self.buffer_size, self.n_envs
         dev = self._device()
         with th.cuda.device(dev):
-            obs = th.from_numpy(np.ascontiguousarray(self.orig_observations)).to(dev).reshape(T * E, -1)
+            # pinned staging + asynchronous copies on the current stream; ONE synchronisation at the end
+            obs = self._h2d("relabel_obs", np.ascontiguousarray(self.orig_observations)).reshape(T * E, -1)
             acs = self.actions
             if not is_discrete(self.action_space):      # the environment (and so the cost wrapper) saw clipped actions
                 acs = np.clip(acs, self.action_space.low, self.action_space.high)
-            acs = th.from_numpy(np.ascontiguousarray(acs, dtype=np.float32)).to(dev).reshape(T * E, -1)
+            acs = self._h2d("relabel_acs", np.ascontiguousarray(acs, dtype=np.float32)).reshape(T * E, -1)
             if is_discrete(self.action_space):
                 acs = acs.reshape(-1)
             orig = constraint_net.cost_function_device(obs, acs).reshape(T, E)
             costs = orig
             vn = cost_normalizer
+            state_h = None
             if vn is not None:
                 state = np.concatenate([[vn.cost_rms.mean, vn.cost_rms.var, vn.cost_rms.count], vn.cost_ret]).astype(np.float64)
-                state_d = th.from_numpy(state).to(dev)
-                dones_d = th.from_numpy(np.ascontiguousarray(self.dones)).to(dev)
-                last_d = th.from_numpy(np.ascontiguousarray(np.asarray(last_dones).astype(np.uint8).reshape(-1))).to(dev)
+                state_d = self._h2d("relabel_state", state)
+                dones_d = self._h2d("relabel_dones", np.ascontiguousarray(self.dones))
+                last_d = self._h2d("relabel_last", np.ascontiguousarray(np.asarray(last_dones).astype(np.uint8).reshape(-1)))
                 costs = th.empty_like(orig)
                 _lib.check(_lib.lib().icrl_cost_normalize(
                     _lib.ptr(orig), _lib.ptr(dones_d), _lib.ptr(last_d), T, E, float(vn.cost_gamma), float(vn.epsilon),
                     float(vn.clip_cost), int(bool(vn.norm_cost)), int(bool(vn.training)), _lib.ptr(state_d),
                     _lib.ptr(costs), _lib.current_stream()))
-                state = state_d.cpu().numpy()
-                if vn.training:
-                    vn.cost_rms.mean, vn.cost_rms.var, vn.cost_rms.count = state[0], state[1], float(state[2])
-                    vn.cost_ret = state[3:].copy()
-            self.orig_costs = orig.cpu().numpy()
-            self.costs = self.orig_costs if costs is orig else costs.cpu().numpy()
+                state_h = self._d2h("relabel_state_out", state_d)
+            orig_h = self._d2h("relabel_orig_out", orig)
+            costs_h = orig_h if costs is orig else self._d2h("relabel_costs_out", costs)
+            th.cuda.current_stream().synchronize()
+            if vn is not None and vn.training:
+                state = state_h.numpy()
+                vn.cost_rms.mean, vn.cost_rms.var, vn.cost_rms.count = state[0], state[1], float(state[2])
+                vn.cost_ret = state[3:].copy()
+            self.orig_costs = orig_h.numpy().copy()
+            self.costs = self.orig_costs if costs is orig else costs_h.numpy().copy()
             if vn is not None:
                 vn.old_cost = self.orig_costs[-1].copy()
+
+    def _h2d(self, name: str, host: np.ndarray) -> th.Tensor:
+        """host array -> persistent pinned staging buffer -> persistent device buffer (asynchronous on the current stream)."""
+        slot = self._stage.get(name)
+        t = th.from_numpy(host)
+        if slot is None or slot[0].shape != t.shape or slot[0].dtype != t.dtype:
+            pinned = th.empty(t.shape, dtype=t.dtype).pin_memory()
+            slot = (pinned, th.empty(t.shape, dtype=t.dtype, device=self._device()))
+            self._stage[name] = slot
+        slot[0].copy_(t)
+        slot[1].copy_(slot[0], non_blocking=True)
+        return slot[1]
+
+    def _d2h(self, name: str, dev_t: th.Tensor) -> th.Tensor:
+        """device tensor -> persistent pinned host buffer (asynchronous: valid after the stream is synchronised)."""
+        slot = self._stage.get(name)
+        if slot is None or slot.shape != dev_t.shape or slot.dtype != dev_t.dtype:
+            slot = th.empty(dev_t.shape, dtype=dev_t.dtype).pin_memory()
+            self._stage[name] = slot
+        slot.copy_(dev_t, non_blocking=True)
+        return slot
 
     def _device(self):
         if self._dev is None:

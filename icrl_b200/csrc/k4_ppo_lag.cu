@@ -283,6 +283,11 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
     return v;
 }
 
+template <int NT1>
+constexpr int ppo_frag_floats() { return NTW2 * 4 + NT1 * 4 + 4 + 1 + 5; }     // F: floats a thread owns in the exchanges
+template <int NT1>
+constexpr int ppo_pay_floats() { return (ppo_frag_floats<NT1>() + 3) / 4 * 4; }   // floats per thread of the pair-exchange buffer
+
 // ---------------------------------------------------------------- the persistent train kernel
 // NT1 = n-tiles of dW1 (64 x KP) each warp owns (warp w: m-tile w & 3, n-tiles (w >> 2) + 2 i).
 // WIDE (large batches): the launch holds a.ncl such clusters and covers ONE epoch.  Every cluster keeps a full replica of the
@@ -303,7 +308,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
     auto range_len = [&](int Bn) { return WIDE ? max(min((cluster_id + 1) * Bc, Bn) - cluster_id * Bc, 0) : Bn; };
     const int LDX = a.DP, KP = a.KP, D = a.D;
     // payload of the pair exchange: gradient fragments + the five loss partial sums (thread 0)
-    constexpr int NP = (NTW2 * 4 + NT1 * 4 + 4 + 1 + 5 + 3) / 4 * 4;
+    constexpr int NP = ppo_pay_floats<NT1>();
     constexpr int PAY_V4 = NTW2 + NT1 + 3;      // float4 groups every thread sends to its partner per step
     static_assert(PAY_V4 * 4 <= NP, "PAY too small");
     const PpoSmem L = ppo_smem_layout(LDX, NP);
@@ -468,9 +473,9 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
     bool stop_all = false;
     const bool timed = (a.timing != nullptr) && tid == 0 && working && cluster_id == 0;
     long long tmark = clock64();
-    unsigned long long tacc[16];
+    unsigned long long tacc[20];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) tacc[i] = 0;
+    for (int i = 0; i < 20; ++i) tacc[i] = 0;
 #define ICRL_MARK(i)                                   \
     if (timed) {                                       \
         const long long now__ = clock64();             \
@@ -974,6 +979,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                     const float4 x = ld4(v4++), y = ld4(v4++);
                     g_s += x.x; tot[0] += x.y; tot[1] += x.z; tot[2] += x.w; tot[3] += y.x; tot[4] += y.y;
                 }
+                ICRL_MARK(16)
                 // ---- (3w) wide mode: sum the pair sums of all clusters (and of all ranks) -- see the kernel's header comment
                 bool exchanged = false;
                 if constexpr (WIDE) {
@@ -1218,8 +1224,22 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                         auto tag = [&](unsigned int x, unsigned int y, unsigned int z) {
                             return want ^ ((x ^ __funnelshift_l(y, y, 11) ^ __funnelshift_l(z, z, 22)) * 0x9E3779B1u);
                         };
+                        // The own contribution never travels through global memory (narrow dW1 tiles, or two ranks): nothing is
+                        // stored to or polled from the own slab, which cuts the bytes every polling round pulls through L2 (the
+                        // rounds are bandwidth bound: 256 threads x words x 16 B per CTA) and the peer stores (~30 B / cycle per
+                        // SM: 825 cycles for HalfCheetah's 24 KB per peer) by 1 / W.  Two ranks: it simply stays in the
+                        // registers (a + b == b + a bit for bit, both ranks form the same sum).  More ranks: it is parked in the
+                        // (idle) pair-exchange buffer and added when the rank-ordered sum reaches this rank's position, so every
+                        // replica still adds the W contributions in rank order.
+                        // (the wide dW1 tiles of NT1 > 2 have no registers to spare for that: own words go through the own slab.
+                        //  Measured and rejected: staging the words in shared memory and sending them as 4 KB TMA bulk stores,
+                        //  shared -> peer global -- send 1153 cycles against 825, profiles/dp2_timing_r02.txt)
+                        constexpr bool SKIP = (W == 2) || (NT1 <= 2);
+                        constexpr bool PARK = SKIP && (W > 2);
+                        float* own = PAY + tid;                       // own[k * NTT]: conflict-free, thread private
 #pragma unroll
                         for (int pr = 0; pr < W; ++pr) {
+                            if (SKIP && pr == me) continue;
                             uint4* dst = slab(a.recv[pr], me);
 #pragma unroll
                             for (int j = 0; j < NWD; ++j) {
@@ -1230,39 +1250,56 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                                 dst[j * NTT] = make_uint4(xi, yi, zi, tag(xi, yi, zi));
                             }
                         }
+                        if (PARK) {
 #pragma unroll
-                        for (int k = 0; k < F; ++k) G(k) = 0.f;
+                            for (int k = 0; k < F; ++k) { own[k * NTT] = G(k); G(k) = 0.f; }
+                        } else if (!SKIP) {
+#pragma unroll
+                            for (int k = 0; k < F; ++k) G(k) = 0.f;
+                        }
+                        ICRL_MARK(17)
                         const long long tstart = clock64();
-                        constexpr int NW = W * NWD;
+                        constexpr int NW = (SKIP ? W - 1 : W) * NWD;   // words of the (remote) ranks, ascending rank
+                        // PW words in flight per polling round trip: every round after the first costs one more L2 round trip
+                        constexpr int PW = NT1 >= 8 ? 16 : (NW <= 26) ? NW : ((NW + 1) / 2 <= 26 ? (NW + 1) / 2 : 16);   // (wide dW1 tiles: no registers to spare)
+                        auto add_own = [&]() {
 #pragma unroll
-                        for (int w0 = 0; w0 < NW; w0 += 16) {
-                            uint4 x[16];
+                            for (int k = 0; k < F; ++k) G(k) += own[k * NTT];
+                        };
+#pragma unroll
+                        for (int w0 = 0; w0 < NW; w0 += PW) {
+                            uint4 x[PW];
                             for (;;) {
                                 bool ok = true;
 #pragma unroll
-                                for (int j = 0; j < 16; ++j)
+                                for (int j = 0; j < PW; ++j)
                                     if (w0 + j < NW) {
-                                        const uint4* src = slab(a.recv[me], (w0 + j) / NWD) + ((w0 + j) % NWD) * NTT;
+                                        const int ri = (w0 + j) / NWD, src_rank = ri + ((SKIP && ri >= me) ? 1 : 0);
+                                        const uint4* src = slab(a.recv[me], src_rank) + ((w0 + j) % NWD) * NTT;
                                         asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
                                                      : "=r"(x[j].x), "=r"(x[j].y), "=r"(x[j].z), "=r"(x[j].w)
                                                      : "l"(src) : "memory");
                                     }
 #pragma unroll
-                                for (int j = 0; j < 16; ++j)
+                                for (int j = 0; j < PW; ++j)
                                     if (w0 + j < NW) ok = ok && (x[j].w == tag(x[j].x, x[j].y, x[j].z));
                                 if (ok) break;
                                 if (clock64() - tstart > 4000000000LL) { XCH[31] = 1.f; break; }   // ~2 s: a peer is gone
                             }
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
+                            for (int j = 0; j < PW; ++j) {
                                 if (w0 + j < NW) {
-                                    const int k = 3 * ((w0 + j) % NWD);       // words ascend rank-major: rank order per element
+                                    // remote rank index ri stands for rank ri + (ri >= me): the own gradient goes in right before
+                                    // the first word of remote index `me` (== rank me + 1)
+                                    if (PARK && (w0 + j) % NWD == 0 && (w0 + j) / NWD == me) add_own();
+                                    const int k = 3 * ((w0 + j) % NWD);
                                     if (k < F) G(k) += __uint_as_float(x[j].x);
                                     if (k + 1 < F) G(k + 1) += __uint_as_float(x[j].y);
                                     if (k + 2 < F) G(k + 2) += __uint_as_float(x[j].z);
                                 }
                             }
                         }
+                        if (PARK && me == W - 1) add_own();
                     };
                     // auto: broadcast + sum for 2 and 4 ranks (measured at 4 ranks: 434 vs 442 ms per iteration against RS/AG),
                     // reduce-scatter + all-gather for 8 (the broadcast would need six polling rounds there)
@@ -1367,6 +1404,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                     }
                 }
             }
+            ICRL_MARK(18)
             // ---- (4) norm of the reduced gradient (block reduction; also publishes the loss totals from scratch[120..124])
             {
                 float r2[6] = {tot[0], tot[1], tot[2], tot[3], tot[4], local_sumsq()};
@@ -1483,7 +1521,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
     if (working && cur_valid(cur)) mbar_wait(&BAR[q & 1], (uint32_t)((q >> 1) & 1));   // drain the in-flight prefetch
     __syncthreads();
     if (timed) {
-        for (int i = 0; i < 16; ++i) a.timing[crank * 16 + i] = tacc[i];
+        for (int i = 0; i < 20; ++i) a.timing[crank * 20 + i] = tacc[i];
     }
 #undef ICRL_MARK
 
@@ -1530,10 +1568,6 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
 }
 
 // ---------------------------------------------------------------- host side
-template <int NT1>
-constexpr int ppo_pay_floats() { return (NTW2 * 4 + NT1 * 4 + 4 + 1 + 5 + 3) / 4 * 4; }
-template <int NT1>
-constexpr int ppo_frag_floats() { return NTW2 * 4 + NT1 * 4 + 4 + 1 + 5; }     // F: floats a thread owns in the exchanges
 
 template <int NT1, bool WIDE>
 static int launch_cfg(const PpoArgs& a, cudaStream_t st, int n_clusters, cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr,
@@ -1774,19 +1808,21 @@ static int ppo_train_impl(const icrl_ppo_cfg* cfg, const icrl_ppo_data* data, fl
 
 // profiling aid (ICRL_PPO_TIMING=1): per-phase cycles of thread 0 of each trunk's first CTA (cluster 0); synchronises!
 static void ppo_print_timing(unsigned long long* timing_dev, cudaStream_t st, double steps) {
-    {
-        unsigned long long h[128];
-        cudaStreamSynchronize(st);
-        cudaMemcpy(h, timing_dev, sizeof(h), cudaMemcpyDeviceToHost);
-        const char* names[11] = {"wait+sync", "prefetch", "L1", "L2", "head", "headgrad+dH2", "dW2+dH1", "dW1", "reduce+stats",
-                                 "xchg+cluster", "adam"};
-        for (int r = 0; r < icrl::NCTA; r += (r == 0 ? 1 : 2)) {
-            fprintf(stderr, "[ppo timing] cta %d cycles/step:", r);
-            double tot = 0;
-            for (int i = 0; i < 11; ++i) { fprintf(stderr, " %s=%.0f", names[i], h[r * 16 + i] / steps); tot += h[r * 16 + i] / steps; }
-            fprintf(stderr, " total=%.0f | of which head: dot=%.0f logp=%.0f, headgrad: dHW=%.0f bias/logstd=%.0f dH2=%.0f\n", tot + (h[r*16+11]+h[r*16+12]+h[r*16+13]+h[r*16+14]+h[r*16+15]) / steps,
-                    h[r * 16 + 11] / steps, h[r * 16 + 12] / steps, h[r * 16 + 13] / steps, h[r * 16 + 14] / steps, h[r * 16 + 15] / steps);
-        }
+    unsigned long long h[128];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, timing_dev, sizeof(h), cudaMemcpyDeviceToHost);
+    const char* names[11] = {"wait+sync", "prefetch", "L1", "L2", "head", "headgrad+dH2", "dW2+dH1", "dW1", "blockreduce+stats",
+                             "norm xchg", "adam"};
+    for (int r = 0; r < icrl::NCTA; r += (r == 0 ? 1 : 2)) {
+        const unsigned long long* t = h + r * 20;
+        fprintf(stderr, "[ppo timing] cta %d cycles/step:", r);
+        double tot = 0;
+        for (int i = 0; i < 11; ++i) { fprintf(stderr, " %s=%.0f", names[i], t[i] / steps); tot += t[i] / steps; }
+        for (int i = 11; i < 19; ++i) tot += t[i] / steps;
+        fprintf(stderr, " | head: dot=%.0f logp=%.0f, headgrad: dHW=%.0f bias/logstd=%.0f dH2=%.0f | exchange: pair wait+add=%.0f "
+                        "rank send=%.0f rank poll+sum=%.0f | total=%.0f\n",
+                t[11] / steps, t[12] / steps, t[13] / steps, t[14] / steps, t[15] / steps, t[16] / steps, t[17] / steps,
+                t[18] / steps, tot);
     }
 }
 

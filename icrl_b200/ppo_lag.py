@@ -216,6 +216,35 @@ class PPOLagrangian:
         self._current_progress_remaining = 1.0 - float(num_timesteps) / float(total_timesteps)
 
     # ---------------------------------------------------------------- K4
+    def _draw_permutations(self, n: int):
+        """One numpy permutation per epoch (buffers.py:596) and the global RNG state after each."""
+        perms = np.empty((self.n_epochs, n), dtype=np.int32)
+        rng_states = []
+        for e in range(self.n_epochs):
+            perms[e] = np.random.permutation(n)
+            rng_states.append(np.random.get_state())
+        return perms, rng_states
+
+    def _speculate_permutations(self, n: int, state_if_all_epochs_run) -> None:
+        """While the kernel runs the host is idle: draw the next train()'s permutations from the state the global numpy RNG
+        will be in if (a) no epoch is cut by target_kl and (b) nobody touches np.random before the next call.  The next
+        call uses them only if the RNG state it finds is exactly that one -- the stream the reference would see is unchanged."""
+        np.random.set_state(state_if_all_epochs_run)
+        perms, states = self._draw_permutations(n)
+        self._spec_perms = (n, self.n_epochs, state_if_all_epochs_run, perms, states)
+
+    def _take_speculated_permutations(self, n: int):
+        spec, self._spec_perms = getattr(self, "_spec_perms", None), None
+        if spec is None or spec[0] != n or spec[1] != self.n_epochs:
+            return None, None
+        now, base = np.random.get_state(), spec[2]
+        same = (now[0] == base[0] and now[2] == base[2] and now[3] == base[3] and now[4] == base[4]
+                and np.array_equal(now[1], base[1]))
+        if not same:
+            return None, None
+        np.random.set_state(spec[4][-1])        # where drawing them now would have left the generator
+        return spec[3], spec[4]
+
     def _stage(self, name: str, host: np.ndarray) -> th.Tensor:
         """host array -> persistent pinned staging buffer -> persistent device buffer (async on the current stream)."""
         slot = self._staging.get(name)
@@ -243,11 +272,9 @@ class PPOLagrangian:
         n = T * E
         # numpy draws one permutation per epoch that actually runs (buffers.py:596); draw them all, remember the RNG
         # state after each, and rewind to the right one once the device reports where it stopped.
-        perms = np.empty((self.n_epochs, n), dtype=np.int32)
-        rng_states = []
-        for e in range(self.n_epochs):
-            perms[e] = np.random.permutation(n)
-            rng_states.append(np.random.get_state())
+        perms, rng_states = self._take_speculated_permutations(n)
+        if perms is None:
+            perms, rng_states = self._draw_permutations(n)
 
         rename = {"log_probs": "old_log_prob", "reward_values": "old_reward_values", "cost_values": "old_cost_values"}
         data = _lib.PpoData()
@@ -296,8 +323,10 @@ class PPOLagrangian:
                     C.byref(cfg), C.byref(data), _lib.ptr(pol._params), _lib.ptr(pol._adam_m), _lib.ptr(pol._adam_v),
                     pol.optimizer.step_count, _lib.ptr(stats), _lib.ptr(result), C.byref(desc), _lib.current_stream()))
         # host work that does not depend on the update overlaps the kernel: the reference's public arrays become
-        # env-major on the first get() (buffers.py:594-611), and the rollout-only logger statistics
+        # env-major on the first get() (buffers.py:594-611), the rollout-only logger statistics, and the NEXT call's
+        # permutations, drawn speculatively from the RNG state this call leaves behind when no epoch is skipped
         buf._flatten_once()
+        self._speculate_permutations(n, rng_states[-1])
         mean_reward_adv = np.mean(buf.reward_advantages.flatten())
         mean_cost_adv = np.mean(buf.cost_advantages.flatten())
         reward_ev = explained_variance(buf.reward_returns.flatten(), buf.reward_values.flatten())

@@ -58,3 +58,39 @@ def test_make_train_env_wrapper_stack():
     assert ev.num_envs == 1 and not ev.training and not ev.norm_reward
     vec_env.sync_envs_normalization(env, ev)
     np.testing.assert_array_equal(ev.obs_rms.mean, env.obs_rms.mean)
+
+
+def test_speculated_permutations_follow_the_numpy_stream():
+    """PPOLagrangian pre-draws the next train()'s permutations while its kernel runs; they are used only when the global
+    RNG is found exactly where the speculation assumed, and then leave the stream where drawing them late would have."""
+    import types
+    from icrl_b200.ppo_lag import PPOLagrangian
+    algo = types.SimpleNamespace(n_epochs=3)
+    for name in ("_draw_permutations", "_speculate_permutations", "_take_speculated_permutations"):
+        setattr(algo, name, types.MethodType(getattr(PPOLagrangian, name), algo))
+    n = 50
+    np.random.seed(7)
+    want1, _ = algo._draw_permutations(n)
+    want2, _ = algo._draw_permutations(n)
+    end_state = np.random.get_state()
+
+    np.random.seed(7)
+    perms1, states1 = algo._draw_permutations(n)
+    algo._speculate_permutations(n, states1[-1])
+    np.random.set_state(states1[-1])                       # train() ran every epoch
+    perms2, states2 = algo._take_speculated_permutations(n)
+    np.testing.assert_array_equal(perms1, want1)
+    np.testing.assert_array_equal(perms2, want2)
+    assert np.array_equal(np.random.get_state()[1], end_state[1]) and np.random.get_state()[2] == end_state[2]
+
+    # an early stop (state rewound to after epoch 1) or any other consumer of np.random invalidates the speculation
+    algo._speculate_permutations(n, states1[-1])
+    np.random.set_state(states1[0])
+    assert algo._take_speculated_permutations(n) == (None, None)
+    algo._speculate_permutations(n, states1[-1])
+    np.random.set_state(states1[-1])
+    np.random.random()
+    assert algo._take_speculated_permutations(n) == (None, None)
+    algo._speculate_permutations(n, states1[-1])
+    np.random.set_state(states1[-1])
+    assert algo._take_speculated_permutations(n + 1) == (None, None)      # another buffer size
