@@ -107,7 +107,7 @@ constexpr int NTW2 = 4;        // n-tiles of a 64 x 64 output per warp (warp til
 
 // ---------------------------------------------------------------- shared memory carve-up (float offsets)
 struct PpoSmem {
-    int w1, w2, b1, b2, hw, hb, logstd, sig, x, h1, h2, dh, rowf, dmean, act, mu, part, bar, scratch, xch, pay, total_bytes;
+    int w1, w2, b1, b2, hw, hb, logstd, sig, x, h1, h2, dh, rowf, dmean, act, mu, part, bar, scratch, tacc, xch, pay, total_bytes;
 };
 __host__ __device__ inline PpoSmem ppo_smem_layout(int LDX, int NP) {
     PpoSmem s;
@@ -131,6 +131,7 @@ __host__ __device__ inline PpoSmem ppo_smem_layout(int LDX, int NP) {
     s.part = o; o += NWT * RBH * AMAX; // per-warp K-slice partials of the action head; later reused as the [16][LDH] dHW staging tile
     s.bar = o; o += 8;               // four 8-byte mbarriers: one per chunk buffer (TMA), pair exchange, norm exchange
     s.scratch = o; o += 128;
+    s.tacc = o; o += 40;             // per-phase cycle counters of thread 0 (ICRL_PPO_TIMING): 20 x 8 bytes
     s.xch = o; o += 2 * 8 * 2;       // [parity][cluster rank][{sumsq, stop}]
     s.pay = o; o += NP * NTT;        // the partner CTA's gradient fragments land here (DSMEM stores)
     s.total_bytes = o * 4;
@@ -288,6 +289,28 @@ constexpr int ppo_frag_floats() { return NTW2 * 4 + NT1 * 4 + 4 + 1 + 5; }     /
 template <int NT1>
 constexpr int ppo_pay_floats() { return (ppo_frag_floats<NT1>() + 3) / 4 * 4; }   // floats per thread of the pair-exchange buffer
 
+template <bool IN_REGS>
+struct TimingCounters;
+template <>
+struct TimingCounters<true> {
+    unsigned long long v[20];
+    __device__ __forceinline__ void init(void*, bool) {
+#pragma unroll
+        for (int i = 0; i < 20; ++i) v[i] = 0;
+    }
+    __device__ __forceinline__ unsigned long long& operator[](int i) { return v[i]; }
+};
+template <>
+struct TimingCounters<false> {
+    unsigned long long* v;
+    __device__ __forceinline__ void init(void* smem, bool timed) {
+        v = reinterpret_cast<unsigned long long*>(smem);
+        if (timed)
+            for (int i = 0; i < 20; ++i) v[i] = 0;
+    }
+    __device__ __forceinline__ unsigned long long& operator[](int i) { return v[i]; }
+};
+
 // ---------------------------------------------------------------- the persistent train kernel
 // NT1 = n-tiles of dW1 (64 x KP) each warp owns (warp w: m-tile w & 3, n-tiles (w >> 2) + 2 i).
 // WIDE (large batches): the launch holds a.ncl such clusters and covers ONE epoch.  Every cluster keeps a full replica of the
@@ -296,7 +319,12 @@ constexpr int ppo_pay_floats() { return (ppo_frag_floats<NT1>() + 3) / 4 * 4; } 
 // cluster order (and, data parallel, exchanges that slice with the peer GPUs' same reducer over NVLink) -> grid barrier ->
 // everybody reads the totals.  All replicas then apply the identical clip + Adam update, so they never diverge.
 template <int NT1, bool DIST, bool WIDE>
-__global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant__ PpoArgs a) {
+#ifdef ICRL_K4_MAXREG       // A/B builds (tools/build_variants.sh): an explicit register cap instead of the launch bounds
+#define ICRL_K4_BOUNDS __maxnreg__(ICRL_K4_MAXREG)
+#else
+#define ICRL_K4_BOUNDS __launch_bounds__(NTT, 1)
+#endif
+__global__ void ICRL_K4_BOUNDS ppo_train_kernel(const __grid_constant__ PpoArgs a) {
     extern __shared__ __align__(16) float sm[];
     if (WIDE && a.result[3] != 0) return;     // an earlier epoch's launch hit the target_kl stop: nothing left to do
     const float nu = a.nu_dev ? *a.nu_dev : a.nu;
@@ -311,6 +339,9 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
     constexpr int NP = ppo_pay_floats<NT1>();
     constexpr int PAY_V4 = NTW2 + NT1 + 3;      // float4 groups every thread sends to its partner per step
     static_assert(PAY_V4 * 4 <= NP, "PAY too small");
+    // bytes a CTA receives per step: every thread's groups, except the last one ({kl, entropy} sums), which only the threads
+    // that own loss partials (hq == 0: every 8th) send
+    constexpr int PAY_BYTES = (PAY_V4 - 1) * NTT * 16 + (NTT / 8) * 16;
     const PpoSmem L = ppo_smem_layout(LDX, NP);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int crank = (int)cluster_ctarank();       // cluster rank: trunk = crank / 2 (0 pi, 1 vf, 2 cvf), half = crank % 2
@@ -456,7 +487,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
     auto fetch_chunk = [&](const Cursor& c, int buf) {   // called by thread 0 only
         const size_t p = (size_t)c.epoch * a.N + (size_t)c.mb * a.B + range_lo(cur_bn(c)) + c.c0 + RBH * half;   // streams carry RB rows of tail padding
         const uint32_t xb = RBH * LDX * 4, sb = RBH * 8 * 4, ab = (role == 0) ? RBH * AP * 4 : 0;
-        fence_proxy_async();   // earlier generic-proxy accesses to this buffer are ordered before the async-proxy writes
+        fence_proxy_async();   // the row buffer takes one generic-proxy write per row (dL/dlogp): order it before the async-proxy writes
         mbar_expect_tx(&BAR[buf], xb + sb + ab);
         bulk_g2s(X + buf * RBH * LDX, a.xs + p * LDX, xb, &BAR[buf]);
         bulk_g2s(ROWF + buf * RBH * 8, a.ss + p * 8, sb, &BAR[buf]);
@@ -473,9 +504,11 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
     bool stop_all = false;
     const bool timed = (a.timing != nullptr) && tid == 0 && working && cluster_id == 0;
     long long tmark = clock64();
-    unsigned long long tacc[20];
-#pragma unroll
-    for (int i = 0; i < 20; ++i) tacc[i] = 0;
+    // per-phase cycle counters of thread 0 (ICRL_PPO_TIMING).  Measured (profiles/k4_variants_r02.txt): the wide dW1 tiles
+    // (NT1 >= 4, AntWall) have no registers to spare -- keeping the 20 counters in shared memory takes 21.5 -> 19.5 us per
+    // optimiser step there -- while the HalfCheetah instantiation is 2 % faster with them in registers.
+    TimingCounters<(NT1 <= 2)> tacc;
+    tacc.init(sm + L.tacc, timed);
 #define ICRL_MARK(i)                                   \
     if (timed) {                                       \
         const long long now__ = clock64();             \
@@ -543,7 +576,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                         // arm this step's exchange barriers.  After the __syncthreads above no thread of this CTA is still
                         // waiting on the previous phase, and bytes that arrive before the arming are accounted for (the
                         // phase cannot complete without this arrival).
-                        mbar_expect_tx(&BAR[2], (uint32_t)(PAY_V4 * NTT * 16));
+                        mbar_expect_tx(&BAR[2], (uint32_t)PAY_BYTES);
                         mbar_expect_tx(&BAR[3], (uint32_t)(NCTA * 8));
                     }
                     ICRL_MARK(0)
@@ -893,7 +926,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                     // no rows of this minibatch fall to this cluster: it still takes part in every exchange (with zeros)
                     __syncthreads();
                     if (tid == 0) {
-                        mbar_expect_tx(&BAR[2], (uint32_t)(PAY_V4 * NTT * 16));
+                        mbar_expect_tx(&BAR[2], (uint32_t)PAY_BYTES);
                         mbar_expect_tx(&BAR[3], (uint32_t)(NCTA * 8));
                     }
 #pragma unroll
@@ -902,11 +935,12 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                 }
             }      // working
 
-            // ---- (1) block-reduce the five loss partial sums of this CTA's rows
+            // ---- (1) block-reduce the five loss partial sums of this CTA's rows (measured: a variant where only warp 0 totals
+            // the per-warp sums -- one barrier, 8 x fewer shared-memory reads -- is no faster: profiles/k4_variants_r02.txt)
             auto block_reduce = [&](float (&r)[6]) {
 #pragma unroll
                 for (int i = 0; i < 6; ++i) r[i] = warp_sum(r[i]);
-                __syncthreads();      // scratch may still be read from the previous use
+                __syncthreads();
                 if (lane == 0) {
 #pragma unroll
                     for (int i = 0; i < 6; ++i) scratch[warp * 8 + i] = r[i];
@@ -954,7 +988,7 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
 #pragma unroll
                 for (int i = 0; i < NT1; ++i) st4(NTW2 + i, g_w1[i][0], g_w1[i][1], g_w1[i][2], g_w1[i][3]);
                 st4(NTW2 + NT1 + 1, g_s, t0 ? tot[0] : 0.f, t0 ? tot[1] : 0.f, t0 ? tot[2] : 0.f);
-                st4(NTW2 + NT1 + 2, t0 ? tot[3] : 0.f, t0 ? tot[4] : 0.f, 0.f, 0.f);
+                if ((tid & 7) == 0) st4(NTW2 + NT1 + 2, tot[3], tot[4], 0.f, 0.f);
             }
             // all of the partner's words of this step have landed (bounded: a vanished partner ends the launch with an error)
             if (*(volatile float*)&XCH[31] == 0.f && !mbar_wait_bounded(&BAR[2], (uint32_t)(step & 1), 2000000000LL)) XCH[31] = 1.f;
@@ -976,8 +1010,12 @@ __global__ void __launch_bounds__(NTT, 1) ppo_train_kernel(const __grid_constant
                     g_hw[0] += x.x; g_hw[1] += x.y; g_hw[2] += x.z; g_hw[3] += x.w;
                 }
                 {
-                    const float4 x = ld4(v4++), y = ld4(v4++);
-                    g_s += x.x; tot[0] += x.y; tot[1] += x.z; tot[2] += x.w; tot[3] += y.x; tot[4] += y.y;
+                    const float4 x = ld4(v4++);
+                    g_s += x.x; tot[0] += x.y; tot[1] += x.z; tot[2] += x.w;
+                    if ((tid & 7) == 0) {
+                        const float4 y = ld4(v4);
+                        tot[3] += y.x; tot[4] += y.y;
+                    }
                 }
                 ICRL_MARK(16)
                 // ---- (3w) wide mode: sum the pair sums of all clusters (and of all ranks) -- see the kernel's header comment
