@@ -1,7 +1,7 @@
 set -u
 export PYTHONPATH=.
 cp icrl_b200/libicrl_b200.so /tmp/orig.so
-for v in base cur; do
+for v in prev cur; do
   cp tools/_variants/$v.so icrl_b200/libicrl_b200.so
   for wl in halfcheetah antwall lapgrid pointcircle; do
     VAR=$v K4_STEPS=0 python - $wl <<'PY'
