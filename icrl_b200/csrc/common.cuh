@@ -139,6 +139,51 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+// ---- warp-level 3xTF32 GEMM on mma.sync m16n8k8 (shared by K4's five GEMMs per chunk and K2's weight gradients)
+// One warp: C[16 x (8 per n-tile)] += A[16 x K] * B[K x .] with 3xTF32.
+//   A element (m, k) at A[m * sam + k * sak]   (A already points at the warp's first row / column)
+//   B element (k, n) at B[k * sbk + n * sbn]
+// n-tile i (i < NT, skipped when ncol0 + i * nstep >= nmax) covers columns ncol0 + i * nstep .. +7.
+// Fragment layout (PTX ISA, m16n8k8 .tf32): g = lane >> 2, t = lane & 3;
+//   a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);  b0 (k = t, n = g) b1 (k = t+4, n = g);
+//   c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
+// GUARD: skip n-tiles at or beyond nmax (a per-tile branch: it keeps ptxas from interleaving the independent MMA chains of
+// different n-tiles, so it is only instantiated where a tile can really fall outside the operand)
+// KPERM: the summation index of a k-step is permuted (slot t <-> k0 + 2t, slot t + 4 <-> k0 + 2t + 1, on BOTH operands, which
+// leaves the product unchanged).  For operands whose K runs along shared-memory ROWS of stride == 4 (mod 32) this turns the
+// 2-way bank conflicts of the natural order (bank 4t + g) into conflict-free loads (banks 8t + g and 8t + 4 + g).
+template <int NT, int KC = 0, bool GUARD = false, bool KPERM = false>
+__device__ __forceinline__ void warp_gemm_3xtf32(float (&c)[NT][4], const float* __restrict__ A, int sam, int sak,
+                                                 const float* __restrict__ B, int sbk, int sbn, int K, int ncol0, int nstep,
+                                                 int nmax, int g, int t) {
+    const int kend = KC > 0 ? KC : K;   // KC > 0: compile-time K, fully unrolled so fragment loads run ahead of the MMAs
+#pragma unroll (KC > 0 ? KC / 8 : 2)
+    for (int k0 = 0; k0 < kend; k0 += 8) {
+        uint32_t ahi[4], alo[4];
+        {
+            const float* ap = A + (k0 + (KPERM ? 2 * t : t)) * sak + g * sam;
+            const int ks = KPERM ? sak : 4 * sak;          // distance between the thread's two K slots
+            split_tf32(ap[0], ahi[0], alo[0]);
+            split_tf32(ap[8 * sam], ahi[1], alo[1]);
+            split_tf32(ap[ks], ahi[2], alo[2]);
+            split_tf32(ap[ks + 8 * sam], ahi[3], alo[3]);
+        }
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            const int n0 = ncol0 + i * nstep;
+            if (!GUARD || n0 < nmax) {
+                uint32_t bhi[2], blo[2];
+                const float* bp = B + (k0 + (KPERM ? 2 * t : t)) * sbk + (n0 + g) * sbn;
+                split_tf32(bp[0], bhi[0], blo[0]);
+                split_tf32(bp[KPERM ? sbk : 4 * sbk], bhi[1], blo[1]);
+                mma_tf32(c[i], alo, bhi);
+                mma_tf32(c[i], ahi, blo);
+                mma_tf32(c[i], ahi, bhi);
+            }
+        }
+    }
+}
+
 // streaming (read-once) global loads that do not pollute L1
 __device__ __forceinline__ float ld_stream(const float* p) {
     float v;

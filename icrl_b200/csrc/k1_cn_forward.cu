@@ -533,7 +533,7 @@ static int launch_pair_cfg(const CnPlan& plan, const void* obs, const float* acs
 template <typename ObsT, int HP>
 static int launch_forward_pair(const CnPlan& plan, const void* obs, const float* acs, int64_t n_rows, float* out,
                                int out_kind, cudaStream_t st) {
-    static const int env_rp = env_int("ICRL_K1_RP", 0), env_nt = env_int("ICRL_K1_NT", 0), env_nbuf = env_int("ICRL_K1_NBUF", 0);
+    const int env_rp = env_int("ICRL_K1_RP", 0), env_nt = env_int("ICRL_K1_NT", 0), env_nbuf = env_int("ICRL_K1_NBUF", 0);
     const int sms = sm_count();
     int rp = 1;      // four rows per thread (RP 2) halves the weight reads again but measured slower: 260 us against 186 (HalfCheetah)
     if (env_rp) rp = (env_rp >= 2 && HP <= 32) ? 2 : 1;
@@ -564,8 +564,8 @@ static int launch_forward_pair(const CnPlan& plan, const void* obs, const float*
 template <typename ObsT, int HP>
 static int launch_forward(const CnPlan& plan, const void* obs, const float* acs, int64_t n_rows, float* out, int out_kind,
                           cudaStream_t st) {
-    static const bool force_ffma = getenv("ICRL_K1_FFMA") != nullptr;       // A/B switches for profiling
-    static const bool force_mma = getenv("ICRL_K1_MMA") != nullptr;
+    const bool force_ffma = getenv("ICRL_K1_FFMA") != nullptr;       // A/B switches for profiling and tests (read per call)
+    const bool force_mma = getenv("ICRL_K1_MMA") != nullptr;
     if (plan.n_hidden <= 2 && force_mma && !force_ffma) {
         bool use_mma = false;
         auto mk = cn_forward_mma_kernel<ObsT, HP>;
@@ -595,11 +595,12 @@ static int launch_forward(const CnPlan& plan, const void* obs, const float* acs,
             return 0;
         }
     }
-    static const bool force_v1 = getenv("ICRL_K1_V1") != nullptr;             // the scalar thread-per-row kernel (A/B runs)
+    const bool force_v1 = getenv("ICRL_K1_V1") != nullptr;             // the scalar thread-per-row kernel (A/B runs)
     // packed kernel where it wins (measured on B200, 4.19 M rows: HalfCheetah 186 us against 203, PointCircle 324 against 516,
     // LapGrid 59 against 60); the wide Ant net (HP 40, 484 B of staging per row) keeps the scalar kernel (2.25 ms against 2.62)
-    static const bool force_pair = getenv("ICRL_K1_PAIR") != nullptr;
-    if (!force_v1 && !force_ffma && (HP <= 32 || force_pair))
+    const bool force_pair = getenv("ICRL_K1_PAIR") != nullptr;
+    // (rollout-sized buffers -- fewer rows than 128 per SM -- keep the scalar kernel too: 12.3 us against 14.3 for 10 240 rows)
+    if (!force_v1 && !force_ffma && ((HP <= 32 && n_rows >= (int64_t)128 * sm_count()) || force_pair))
         return launch_forward_pair<ObsT, HP>(plan, obs, acs, n_rows, out, out_kind, st);
     auto kern = cn_forward_kernel<ObsT, HP>;
     // pick the largest tile (== block size) whose shared memory fits

@@ -52,51 +52,6 @@ __device__ __forceinline__ void st_remote_f32(float* local_ptr, uint32_t rank, f
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
 }
 
-// ---------------------------------------------------------------- tensor-core helpers (mma.sync m16n8k8, TF32, fp32 accumulate)
-// One warp: C[16 x (8 per n-tile)] += A[16 x K] * B[K x .] with 3xTF32.
-//   A element (m, k) at A[m * sam + k * sak]   (A already points at the warp's first row / column)
-//   B element (k, n) at B[k * sbk + n * sbn]
-// n-tile i (i < NT, skipped when ncol0 + i * nstep >= nmax) covers columns ncol0 + i * nstep .. +7.
-// Fragment layout (PTX ISA, m16n8k8 .tf32): g = lane >> 2, t = lane & 3;
-//   a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);  b0 (k = t, n = g) b1 (k = t+4, n = g);
-//   c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
-// GUARD: skip n-tiles at or beyond nmax (a per-tile branch: it keeps ptxas from interleaving the independent MMA chains of
-// different n-tiles, so it is only instantiated where a tile can really fall outside the operand)
-// KPERM: the summation index of a k-step is permuted (slot t <-> k0 + 2t, slot t + 4 <-> k0 + 2t + 1, on BOTH operands, which
-// leaves the product unchanged).  For operands whose K runs along shared-memory ROWS of stride == 4 (mod 32) this turns the
-// 2-way bank conflicts of the natural order (bank 4t + g) into conflict-free loads (banks 8t + g and 8t + 4 + g).
-template <int NT, int KC = 0, bool GUARD = false, bool KPERM = false>
-__device__ __forceinline__ void warp_gemm_3xtf32(float (&c)[NT][4], const float* __restrict__ A, int sam, int sak,
-                                                 const float* __restrict__ B, int sbk, int sbn, int K, int ncol0, int nstep,
-                                                 int nmax, int g, int t) {
-    const int kend = KC > 0 ? KC : K;   // KC > 0: compile-time K, fully unrolled so fragment loads run ahead of the MMAs
-#pragma unroll (KC > 0 ? KC / 8 : 2)
-    for (int k0 = 0; k0 < kend; k0 += 8) {
-        uint32_t ahi[4], alo[4];
-        {
-            const float* ap = A + (k0 + (KPERM ? 2 * t : t)) * sak + g * sam;
-            const int ks = KPERM ? sak : 4 * sak;          // distance between the thread's two K slots
-            split_tf32(ap[0], ahi[0], alo[0]);
-            split_tf32(ap[8 * sam], ahi[1], alo[1]);
-            split_tf32(ap[ks], ahi[2], alo[2]);
-            split_tf32(ap[ks + 8 * sam], ahi[3], alo[3]);
-        }
-#pragma unroll
-        for (int i = 0; i < NT; ++i) {
-            const int n0 = ncol0 + i * nstep;
-            if (!GUARD || n0 < nmax) {
-                uint32_t bhi[2], blo[2];
-                const float* bp = B + (k0 + (KPERM ? 2 * t : t)) * sbk + (n0 + g) * sbn;
-                split_tf32(bp[0], bhi[0], blo[0]);
-                split_tf32(bp[KPERM ? sbk : 4 * sbk], bhi[1], blo[1]);
-                mma_tf32(c[i], alo, bhi);
-                mma_tf32(c[i], ahi, blo);
-                mma_tf32(c[i], ahi, bhi);
-            }
-        }
-    }
-}
-
 // ---------------------------------------------------------------- geometry of the train kernel
 constexpr int NHALF = 2;       // CTAs per trunk: each takes RBH rows of every 64-row chunk (a CTA pair)
 constexpr int RBH = RB / NHALF;
@@ -1064,16 +1019,23 @@ __global__ void ICRL_K4_BOUNDS ppo_train_kernel(const __grid_constant__ PpoArgs 
                     {
                         float rs[WIDE_SMAX];
                         const float* pbase = a.wide_part + ((size_t)role * ncl * F) * NTT + tid;
+                        // (latency bound: 4 clusters x S floats = up to 24 independent L2 loads in flight per round trip instead
+                        //  of 8 -- the reduction was ~10 k cycles per step, 10 % of the samples of a 1 M-row launch)
 #pragma unroll
-                        for (int kk = 0; kk < WIDE_SMAX; ++kk) {
-                            rs[kk] = 0.f;
-                            const int k = rid * S + kk;
-                            if (kk < S && k < F) {
-                                float acc = 0.f;
-#pragma unroll 8
-                                for (int c = 0; c < ncl; ++c) acc += __ldcg(pbase + ((size_t)c * F + k) * NTT);   // cluster order
-                                rs[kk] = acc;
-                            }
+                        for (int kk = 0; kk < WIDE_SMAX; ++kk) rs[kk] = 0.f;
+                        for (int c0 = 0; c0 < ncl; c0 += 4) {
+                            float v[4][WIDE_SMAX];
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+                                for (int kk = 0; kk < WIDE_SMAX; ++kk) {
+                                    const int k = rid * S + kk;
+                                    v[cc][kk] = (c0 + cc < ncl && kk < S && k < F) ? __ldcg(pbase + ((size_t)(c0 + cc) * F + k) * NTT) : 0.f;
+                                }
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc)          // cluster order per float: identical bits on every replica
+#pragma unroll
+                                for (int kk = 0; kk < WIDE_SMAX; ++kk) rs[kk] += v[cc][kk];
                         }
                         if (DIST && a.world > 1) {
                             // data parallel: the same reducer of every rank holds the same slice -> one-hop exchange of

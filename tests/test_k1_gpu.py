@@ -143,6 +143,44 @@ def test_tensor_core_variant_matches_goldens():
     assert " passed" in r.stdout
 
 
+def test_packed_kernel_matches_goldens():
+    """The packed-FP32 kernel (FFMA2, two rows per thread, double-buffered TMA tiles) is the default only for buffers of
+    >= 128 rows per SM and nets up to 32 wide; ICRL_K1_PAIR=1 forces it everywhere (every width, ragged and unaligned
+    tiles, float64 observations, normalisation, one-hot actions) against the same goldens."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("ICRL_K1_PAIR_CHILD"):
+        pytest.skip("already inside the child run")
+    env = dict(os.environ, ICRL_K1_PAIR="1", ICRL_K1_PAIR_CHILD="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-x", "-k",
+                        "golden or checkpoint or ragged or 3d or unaligned or large"],
+                       env=env, capture_output=True, text=True, timeout=600, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
+
+
+@pytest.mark.parametrize("shape", ["hc", "lgw", "ant", "point"])
+@pytest.mark.parametrize("n", [77, 50_000])
+def test_packed_kernel_is_bit_identical_to_the_scalar_kernel(shape, n, monkeypatch):
+    """Same IEEE fma sequence per row (bias + sum over k in order): the two kernels must agree bit for bit."""
+    if shape not in SHAPES:
+        pytest.skip(f"no {shape} shape")
+    d = load_golden(f"k1_{shape}_norm_f32")
+    s = SHAPES[shape]
+    cn = make_cn(shape, d)
+    rng = np.random.default_rng(n)
+    obs = (rng.standard_normal((n, s["obs_dim"])) * 6).astype(np.float32)
+    acs = (rng.integers(0, s["acs_dim"], (n, 1)).astype(np.float32) if s["is_discrete"]
+           else rng.standard_normal((n, s["acs_dim"])).astype(np.float32) * 1.5)
+    monkeypatch.setenv("ICRL_K1_V1", "1")
+    scalar = cn.cost_function(obs, acs)
+    monkeypatch.delenv("ICRL_K1_V1")
+    monkeypatch.setenv("ICRL_K1_PAIR", "1")
+    packed = cn.cost_function(obs, acs)
+    np.testing.assert_array_equal(packed, scalar)
+
+
 @pytest.mark.parametrize("name", ["antbroken", "point"])
 def test_gail_discriminator_reward_function(name):
     """`cpg --load_gail`: the reference's shipped discriminators loaded by GailDiscriminator.load, evaluated by K1

@@ -31,7 +31,7 @@ ncu)
         python tools/k4_wide_time.py antwall 1048576 13107 2 > $OUT/ncu_k4wide_$R.log 2>&1
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:dual_gae_kernel -s 2 -c 4 -f -o $OUT/k3_$R \
         python tools/profile_target.py k3 > $OUT/ncu_k3_$R.log 2>&1
-    timeout 600 ncu --set full --clock-control none --import-source on -k regex:cn_forward_kernel -s 2 -c 4 -f -o $OUT/k1_$R \
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:cn_forward -s 2 -c 4 -f -o $OUT/k1_$R \
         python tools/profile_target.py k1 > $OUT/ncu_k1_$R.log 2>&1
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:cn_grad_kernel -s 1 -c 1 -f -o $OUT/k2_$R \
         python tools/profile_target.py k2 > $OUT/ncu_k2_$R.log 2>&1
