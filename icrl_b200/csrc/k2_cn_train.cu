@@ -143,13 +143,17 @@ __global__ void __launch_bounds__(256) cn_is_partial_kernel(CnCtrl* ctrl, const 
             for (int r = 0; r < x.world; ++r) x.prod(r)[episode_base + j] = pj;
         }
     }
-    if (cn_last_block(&ctrl->ticket[0]) && tid == 0) {
+    if (cn_last_block(&ctrl->ticket[0]) && tid < 32) {
+        // warp 0 of the last block: lanes stride over the CTA partials (independent L2 loads), shuffle tree in a fixed order
         double tot = 0.0;
-        for (unsigned int b = 0; b < gridDim.x; ++b) tot += *(volatile double*)&part[b];
-        for (int r = 0; r < x.world; ++r) x.hdr(r)->sum_ratio[x.rank] = tot;
-        __threadfence_system();
-        for (int r = 0; r < x.world; ++r) cn_st_release_sys(&x.hdr(r)->flags[0][x.rank], want);
-        ctrl->ticket[0] = 0;
+        for (unsigned int b = tid; b < gridDim.x; b += 32) tot += *(volatile double*)&part[b];
+        tot = warp_sum(tot);
+        if (tid == 0) {
+            for (int r = 0; r < x.world; ++r) x.hdr(r)->sum_ratio[x.rank] = tot;
+            __threadfence_system();
+            for (int r = 0; r < x.world; ++r) cn_st_release_sys(&x.hdr(r)->flags[0][x.rank], want);
+            ctrl->ticket[0] = 0;
+        }
     }
 }
 
@@ -232,12 +236,20 @@ __global__ void __launch_bounds__(256) cn_is_weights_kernel(CnCtrl* ctrl, const 
         double* o = part + (size_t)blockIdx.x * 4;
         o[0] = ws; o[1] = (double)mx; o[2] = (double)mn; o[3] = nn ? 1.0 : 0.0;
     }
-    if (cn_last_block(&ctrl->ticket[1]) && tid == 0) {
+    if (cn_last_block(&ctrl->ticket[1]) && tid < 32) {
         double tot = 0.0, mx = -INFINITY, mn = INFINITY, nn = 0.0;
-        for (unsigned int b = 0; b < gridDim.x; ++b) {
+        for (unsigned int b = tid; b < gridDim.x; b += 32) {
             const volatile double* o = part + (size_t)b * 4;
             tot += o[0]; mx = fmax(mx, o[1]); mn = fmin(mn, o[2]); nn += o[3];
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            nn += __shfl_xor_sync(0xffffffffu, nn, o);
+        }
+        if (tid != 0) return;
         for (int r = 0; r < x.world; ++r) {
             double* d = x.hdr(r)->wstat[x.rank];
             d[0] = tot; d[1] = mx; d[2] = mn; d[3] = nn;
@@ -607,21 +619,32 @@ __global__ void __launch_bounds__(256) cn_reduce_kernel(CnCtrl* ctrl, const CnX 
                                                         const float* __restrict__ part_stats, int n_parts, int n_params,
                                                         unsigned int want) {
     if (ctrl->stopped) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // a WARP per parameter: lane l adds the partials of CTAs l, l + 32, ... and a shuffle tree totals the lanes (a fixed order
+    // for a given n_parts).  One thread per parameter walked the n_parts partials as one dependent chain of L2 loads:
+    // 80 us per launch for 119 partials, more than the gradient kernel itself.
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int i = blockIdx.x * 8 + wib;
     if (i < n_params) {
         float g = 0.f;
-        for (int b = 0; b < n_parts; ++b) g += part_grad[(size_t)b * n_params + i];
-        for (int r = 0; r < x.world; ++r) x.grad(r, x.rank)[i] = g;
+        for (int b = lane; b < n_parts; b += 32) g += part_grad[(size_t)b * n_params + i];
+        g = warp_sum(g);
+        if (lane < x.world) x.grad(lane, x.rank)[i] = g;
     }
-    if (blockIdx.x == 0 && threadIdx.x < ST_COUNT) {
-        const int k = threadIdx.x;
-        const bool is_max = (k == ST_NMAX || k == ST_EMAX), is_min = (k == ST_NMIN || k == ST_EMIN);
-        double v = is_max ? -INFINITY : is_min ? INFINITY : 0.0;
-        for (int b = 0; b < n_parts; ++b) {
-            const double p = (double)part_stats[(size_t)b * ST_COUNT + k];
-            v = is_max ? fmax(v, p) : is_min ? fmin(v, p) : v + p;
+    if (blockIdx.x == 0) {
+        for (int k = wib; k < ST_COUNT; k += 8) {
+            const bool is_max = (k == ST_NMAX || k == ST_EMAX), is_min = (k == ST_NMIN || k == ST_EMIN);
+            double v = is_max ? -INFINITY : is_min ? INFINITY : 0.0;
+            for (int b = lane; b < n_parts; b += 32) {
+                const double p = (double)part_stats[(size_t)b * ST_COUNT + k];
+                v = is_max ? fmax(v, p) : is_min ? fmin(v, p) : v + p;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double q = __shfl_xor_sync(0xffffffffu, v, o);
+                v = is_max ? fmax(v, q) : is_min ? fmin(v, q) : v + q;
+            }
+            if (lane < x.world) x.hdr(lane)->stats[x.rank][k] = v;
         }
-        for (int r = 0; r < x.world; ++r) x.hdr(r)->stats[x.rank][k] = v;
     }
     if (cn_last_block(&ctrl->ticket[2]) && threadIdx.x == 0) {
         for (int r = 0; r < x.world; ++r) cn_st_release_sys(&x.hdr(r)->flags[2][x.rank], want);
@@ -872,7 +895,7 @@ static int cn_train_impl(const icrl_cn_desc* d, const icrl_cn_train_cfg* cfg, co
                                             n_params, &part_grad, &part_stats, &n_parts, st);
             if (rc) return rc;
             const unsigned int want2 = seq_base + (unsigned int)step_index + 1u;
-            cn_reduce_kernel<<<pgrid, 256, 0, st>>>(ctrl, x, part_grad, part_stats, n_parts, n_params, want2);
+            cn_reduce_kernel<<<(n_params + 7) / 8, 256, 0, st>>>(ctrl, x, part_grad, part_stats, n_parts, n_params, want2);
             ICRL_LAUNCH_CHECK();
             cn_adam_kernel<<<pgrid, 256, 0, st>>>(ctrl, x, const_cast<float*>(plan.params), adam_m, adam_v, n_params,
                                                   gc.n_nom_global, gc.n_exp_global, n_nom_global, use_is, per_step,
