@@ -734,11 +734,38 @@ def run_workload(name, args, rank, world, local, ppo_comm, peaks, flush, steps, 
                       "path": "RolloutBufferWithCost.relabel_costs (or ConstraintNet.cost_function) / compute_returns_and_advantage"
                               " / PPOLagrangian.train / ConstraintNet.train with numpy buffers (pinned staging + async H2D, "
                               "D2H of costs, advantages, per-step stats, metrics)"}
+    if dp:
+        # soak evidence for the fence-less, self-validating NVLink exchange: after every warm-up + timed step of BOTH legs the
+        # replicated parameters and Adam moments (policy and constraint net) must still be bit-identical on all ranks
+        per_iter = w.rollouts * learner.steps_taken_per_rollout()
+        tensors = [learner.policy._params, learner.policy._adam_m, learner.policy._adam_v, learner.cn._params,
+                   learner.cn._adam_m, learner.cn._adam_v]
+        n_exchanged = (warmup + steps) * per_iter
+        if want_e2e:
+            pol = hl.algo.policy
+            tensors += [pol._params, pol._adam_m, pol._adam_v]
+            n_exchanged += (2 + steps) * per_iter
+        same = replicas_identical(tensors, world)
+        out["replicas"] = {"bit_identical_after_run": same, "k4_exchange_steps": int(n_exchanged),
+                           "k2_exchange_iterations": int((warmup + steps + (2 + steps if want_e2e else 0)) * w.backward_iters)}
+        if not same:
+            raise SystemExit(f"data-parallel replicas DIVERGED during the {name} run: {out['replicas']}")
     if rank == 0:
         out["roofline"] = kernel_roofline(learner, peaks)
         if want_family:
             out["kernels"] = family_rooflines(learner, peaks)
     return out, learner
+
+
+def replicas_identical(tensors, world):
+    """Data parallel: every rank must hold bit-identical copies of `tensors` (two order-sensitive 64-bit digests, all-gathered)."""
+    import torch.distributed as dist
+    flat = th.cat([t.detach().reshape(-1).view(th.int32).to(th.int64) for t in tensors])
+    weights = th.arange(flat.numel(), device=flat.device, dtype=th.int64) % 65521 + 1
+    h = th.stack([flat.sum(), (flat * weights).sum()])
+    got = [th.zeros_like(h) for _ in range(world)]
+    dist.all_gather(got, h)
+    return all(bool((g == got[0]).all()) for g in got)
 
 
 def all_peaks():
@@ -819,7 +846,10 @@ def main():
             "clocks": main_out["clocks"], "e2e": main_out.get("e2e"), "gpu_launches": main_out["gpu_launches"],
             "roofline": main_out.get("roofline"), "kernels": main_out.get("kernels"), "peaks": peaks,
             "dp_parity": None if dp_parity is None else {"ok": True, "checks": dp_parity,
-                                                          "max_param_err": max(p["max_param_err"] for p in dp_parity)},
+                                                          "max_param_err": max(p["max_param_err"] for p in dp_parity),
+                                                          "replicas_after_timed_runs": {
+                                                              **{args.workload: main_out.get("replicas")},
+                                                              **{k: v.get("replicas") for k, v in others.items()}}},
             "workloads": others, "sweep": sweep, "cpu_baseline": cpu}))
     if ppo_comm is not None:
         ppo_comm.close()
