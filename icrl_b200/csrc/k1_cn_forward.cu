@@ -6,10 +6,14 @@
 // 2*n_select*h1 flops per row, so LGW/HC shapes are HBM-bound and Ant (121->40->40->1, 27 flop/B) is
 // FP32-FMA-bound on CUDA cores.  Persistent grid: (resident CTAs per SM) x (SM count) CTAs loop over tiles.
 #include <stdlib.h>
+#include <string.h>
 
 #include "cn_common.cuh"
 
 namespace icrl {
+
+// cleared around launches whose inputs live in host-mapped pinned memory (the small-batch host path): plain loads, no bulk copies
+static thread_local bool g_k1_allow_tma = true;
 
 int cn_padded_width(const CnPlan& p) {
     int m = 1;
@@ -97,6 +101,74 @@ __global__ void __launch_bounds__(128) cn_forward_kernel(const __grid_constant__
             out[row0 + r] = out_kind == 0 ? 1.0f - pr : pr;
         }
         __syncthreads();   // everyone is done with the staged tile before it is overwritten
+    }
+}
+
+// ---------------------------------------------------------------- tiny batches: one CTA per row, one thread per hidden unit
+// The per-environment-step cost call hands over [n_envs, .] rows (5 in every shipped config).  With a thread per ROW those few
+// threads walk the whole MLP serially (AntWall: 6 480 dependent-issue FMAs, ~35 us for 5 rows); here thread j owns hidden unit j
+// and reads its weight row straight from the flat parameter vector (L2 resident), the inputs and activations of the row pass
+// through shared memory.  Same fma order per unit (bias, then k ascending) and a serial output dot: bit-identical results.
+template <typename ObsT>
+__device__ __forceinline__ float cn_input_global(const CnPlan& p, const ObsT* __restrict__ orow, const float* __restrict__ arow, int k) {
+    const int s = p.sel[k];
+    if (s < p.obs_dim) {
+        const ObsT o = orow[s];
+        if (p.has_norm) {
+            double t = ((double)o - p.mean[s]) * p.rstd[s];
+            if (p.has_clip_obs) t = fmin(fmax(t, -p.clip_obs), p.clip_obs);
+            return (float)t;
+        }
+        if (sizeof(ObsT) == 8) {
+            double t = (double)o;
+            if (p.has_clip_obs) t = fmin(fmax(t, -p.clip_obs), p.clip_obs);
+            return (float)t;
+        }
+        float t = (float)o;
+        if (p.has_clip_obs) t = fminf(fmaxf(t, -(float)p.clip_obs), (float)p.clip_obs);
+        return t;
+    }
+    const int j = s - p.obs_dim;
+    if (p.is_discrete) return ((int)arow[0] == j) ? 1.f : 0.f;
+    float a = arow[j];
+    if (p.has_clip_acs) a = fminf(fmaxf(a, p.low[j]), p.high[j]);
+    return a;
+}
+
+template <typename ObsT>
+__global__ void __launch_bounds__(ICRL_CN_MAX_WIDTH) cn_forward_small_kernel(const __grid_constant__ CnPlan plan,
+                                                                              const ObsT* __restrict__ obs,
+                                                                              const float* __restrict__ acs,
+                                                                              float* __restrict__ out, int out_kind) {
+    __shared__ float X[ICRL_MAX_SELECT];
+    __shared__ float Hs[2][ICRL_CN_MAX_WIDTH];
+    const int row = blockIdx.x, j = threadIdx.x;
+    const ObsT* orow = obs + (size_t)row * plan.obs_dim;
+    const float* arow = acs + (size_t)row * plan.acs_w;
+    for (int k = j; k < plan.n_select; k += blockDim.x) X[k] = cn_input_global<ObsT>(plan, orow, arow, k);
+    __syncthreads();
+    const float* src = plan.params;
+    int in_dim = plan.n_select;
+    const float* in = X;
+    for (int l = 0; l < plan.n_hidden; ++l) {
+        const int out_dim = plan.hidden[l];
+        if (j < out_dim) {
+            const float* wrow = src + (size_t)j * in_dim;
+            float acc = src[(size_t)out_dim * in_dim + j];
+#pragma unroll 4
+            for (int k = 0; k < in_dim; ++k) acc = fmaf(in[k], wrow[k], acc);
+            Hs[l & 1][j] = fmaxf(acc, 0.f);
+        }
+        __syncthreads();
+        src += (size_t)out_dim * in_dim + out_dim;
+        in_dim = out_dim;
+        in = Hs[l & 1];
+    }
+    if (j == 0) {
+        float z = src[in_dim];
+        for (int k = 0; k < in_dim; ++k) z = fmaf(in[k], src[k], z);
+        const float pr = sigmoidf_ref(z);
+        out[row] = out_kind == 0 ? 1.0f - pr : pr;
     }
 }
 
@@ -521,7 +593,7 @@ static int launch_pair_cfg(const CnPlan& plan, const void* obs, const float* acs
     const int tile = 2 * RP * nt;
     const int64_t n_tiles = (n_rows + tile - 1) / tile;
     const int grid = (int)((n_tiles < (int64_t)per_sm * sm_count()) ? n_tiles : (int64_t)per_sm * sm_count());
-    const int tma_ok = ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(acs)) & 15u) == 0 &&
+    const int tma_ok = g_k1_allow_tma && ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(acs)) & 15u) == 0 &&
                        (tile * plan.obs_dim * sizeof(ObsT)) % 16 == 0 && (tile * plan.acs_w * 4) % 16 == 0;
     kern<<<grid, nt, L.total, st>>>(plan, static_cast<const ObsT*>(obs), acs, n_rows, out, out_kind, tma_ok, nbuf);
     ICRL_LAUNCH_CHECK();
@@ -589,7 +661,7 @@ static int launch_forward(const CnPlan& plan, const void* obs, const float* acs,
             if (per_sm < 1) per_sm = 1;
             const int64_t n_tiles = (n_rows + 127) / 128;
             const int grid = (int)((n_tiles < (int64_t)per_sm * sm_count()) ? n_tiles : (int64_t)per_sm * sm_count());
-            const int tma_ok = ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(acs)) & 15u) == 0;
+            const int tma_ok = g_k1_allow_tma && ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(acs)) & 15u) == 0;
             mk<<<grid, 128, Lm.total, st>>>(plan, static_cast<const ObsT*>(obs), acs, n_rows, out, out_kind, tma_ok);
             ICRL_LAUNCH_CHECK();
             return 0;
@@ -620,7 +692,7 @@ static int launch_forward(const CnPlan& plan, const void* obs, const float* acs,
     if (per_sm < 1) per_sm = 1;
     const int64_t n_tiles = (n_rows + tile - 1) / tile;
     const int grid = (int)((n_tiles < (int64_t)per_sm * sm_count()) ? n_tiles : (int64_t)per_sm * sm_count());
-    const int tma_ok = ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(acs)) & 15u) == 0;
+    const int tma_ok = g_k1_allow_tma && ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(acs)) & 15u) == 0;
     kern<<<grid, tile, L.total, st>>>(plan, static_cast<const ObsT*>(obs), acs, n_rows, out, out_kind, tma_ok);
     ICRL_LAUNCH_CHECK();
     return 0;
@@ -645,6 +717,17 @@ static int dispatch_width(const CnPlan& plan, const void* obs, const float* acs,
 int cn_forward_device(const CnPlan& plan, const void* obs, int obs_is_f64, const float* acs, int64_t n_rows, float* out,
                       int out_kind, cudaStream_t st) {
     if (n_rows == 0) return 0;
+    if (n_rows <= 16 && getenv("ICRL_K1_NO_SMALL") == nullptr) {          // a cost-wrapper call: one CTA per row, thread per unit
+        int width = 32;
+        for (int l = 0; l < plan.n_hidden; ++l) width = plan.hidden[l] > width ? plan.hidden[l] : width;
+        width = (width + 31) / 32 * 32;
+        if (obs_is_f64)
+            cn_forward_small_kernel<double><<<(int)n_rows, width, 0, st>>>(plan, static_cast<const double*>(obs), acs, out, out_kind);
+        else
+            cn_forward_small_kernel<float><<<(int)n_rows, width, 0, st>>>(plan, static_cast<const float*>(obs), acs, out, out_kind);
+        ICRL_LAUNCH_CHECK();
+        return 0;
+    }
     return obs_is_f64 ? dispatch_width<double>(plan, obs, acs, n_rows, out, out_kind, st)
                       : dispatch_width<float>(plan, obs, acs, n_rows, out, out_kind, st);
 }
@@ -682,6 +765,26 @@ int icrl_cn_forward_host(const icrl_cn_desc* d, const void* obs, int32_t obs_is_
     cudaStream_t st = (cudaStream_t)stream;
     const size_t ob = (size_t)n_rows * p.obs_dim * (obs_is_f64 ? 8 : 4), ab = (size_t)n_rows * p.acs_w * 4,
                  cb = (size_t)n_rows * 4;
+    if (ob + ab + cb <= 64 * 1024 && getenv("ICRL_K1_NO_ZEROCOPY") == nullptr) {
+        // Small batches -- the per-environment-step calls of VecCostWrapper.step_wait ([n_envs, .] rows, 2048 per rollout): three
+        // staged copies + a synchronisation cost ~45 us per call on the host.  Instead the kernel reads the rows from, and
+        // writes the costs to, one host-mapped pinned block (UVA: the device addresses it directly over PCIe): one launch, one
+        // synchronisation.
+        const size_t o_acs = (ob + 15) / 16 * 16, o_out = o_acs + (ab + 15) / 16 * 16;
+        void* pin;
+        if ((rc = icrl::pinned_scratch(icrl::SLOT_IN0, o_out + cb, &pin))) return rc;
+        unsigned char* base = static_cast<unsigned char*>(pin);
+        memcpy(base, obs, ob);
+        memcpy(base + o_acs, acs, ab);
+        icrl::g_k1_allow_tma = false;
+        rc = icrl::cn_forward_device(p, base, obs_is_f64, reinterpret_cast<const float*>(base + o_acs), n_rows,
+                                     reinterpret_cast<float*>(base + o_out), out_kind, st);
+        icrl::g_k1_allow_tma = true;
+        if (rc) return rc;
+        ICRL_CUDA(cudaStreamSynchronize(st));
+        memcpy(out, base + o_out, cb);
+        return 0;
+    }
     void *dobs, *dacs, *dout;
     if ((rc = icrl::device_scratch(icrl::SLOT_IN0, ob, &dobs))) return rc;
     if ((rc = icrl::device_scratch(icrl::SLOT_IN1, ab, &dacs))) return rc;

@@ -161,9 +161,10 @@ def test_packed_kernel_matches_goldens():
 
 
 @pytest.mark.parametrize("shape", ["hc", "lgw", "ant", "point"])
-@pytest.mark.parametrize("n", [77, 50_000])
+@pytest.mark.parametrize("n", [5, 16, 77, 50_000])
 def test_packed_kernel_is_bit_identical_to_the_scalar_kernel(shape, n, monkeypatch):
-    """Same IEEE fma sequence per row (bias + sum over k in order): the two kernels must agree bit for bit."""
+    """Same IEEE fma sequence per row (bias + sum over k in order): the scalar kernel, the packed kernel and the tiny-batch
+    kernel of the per-environment-step calls (n <= 16: one CTA per row, one thread per hidden unit) must agree bit for bit."""
     if shape not in SHAPES:
         pytest.skip(f"no {shape} shape")
     d = load_golden(f"k1_{shape}_norm_f32")
@@ -174,11 +175,17 @@ def test_packed_kernel_is_bit_identical_to_the_scalar_kernel(shape, n, monkeypat
     acs = (rng.integers(0, s["acs_dim"], (n, 1)).astype(np.float32) if s["is_discrete"]
            else rng.standard_normal((n, s["acs_dim"])).astype(np.float32) * 1.5)
     monkeypatch.setenv("ICRL_K1_V1", "1")
+    monkeypatch.setenv("ICRL_K1_NO_SMALL", "1")
     scalar = cn.cost_function(obs, acs)
     monkeypatch.delenv("ICRL_K1_V1")
     monkeypatch.setenv("ICRL_K1_PAIR", "1")
     packed = cn.cost_function(obs, acs)
     np.testing.assert_array_equal(packed, scalar)
+    if n <= 16:
+        monkeypatch.delenv("ICRL_K1_NO_SMALL")
+        np.testing.assert_array_equal(cn.cost_function(obs, acs), scalar)                       # tiny-batch kernel, zero-copy path
+        monkeypatch.setenv("ICRL_K1_NO_ZEROCOPY", "1")
+        np.testing.assert_array_equal(cn.cost_function(obs, acs), scalar)                       # ... through staged copies
 
 
 @pytest.mark.parametrize("name", ["antbroken", "point"])
