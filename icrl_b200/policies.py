@@ -167,33 +167,82 @@ class ActorTwoCriticsPolicy:
                                                       _lib.current_stream()))
         return head, values, cost_values
 
-    def _dist_terms(self, head: th.Tensor, actions: th.Tensor):
+    def _dist_terms(self, head: th.Tensor, actions: th.Tensor, log_std: Optional[th.Tensor] = None):
         """log_prob / entropy with torch.distributions' formulas (distributions.py:143-167, 274-282)."""
         if self.is_discrete:
             logits = head - head.logsumexp(dim=-1, keepdim=True)
             log_prob = logits.gather(-1, actions.long().reshape(-1, 1)).squeeze(-1)
             entropy = -(th.clamp(logits, min=th.finfo(logits.dtype).min) * logits.exp()).sum(-1)
         else:
-            scale = th.ones_like(head) * self.log_std.to(head.device).exp()
+            scale = th.ones_like(head) * (self.log_std if log_std is None else log_std).to(head.device).exp()
             log_scale = scale.log()
             log_prob = (-((actions - head) ** 2) / (2 * scale ** 2) - log_scale - math.log(math.sqrt(2 * math.pi))).sum(1)
             entropy = (0.5 + 0.5 * math.log(2 * math.pi) + log_scale).sum(1)
         return log_prob, entropy
 
+    def _forward_heads_small(self, obs: th.Tensor):
+        """Rollout-time call ([n_envs, obs_dim] host rows, once per environment step): the kernel reads the rows from, and
+        writes heads / values to, one host-mapped pinned block (UVA), log_std rides along as a 4*A-byte async copy: one launch
+        and ONE synchronisation instead of an upload, three allocations and four blocking downloads.  Returns host tensors."""
+        n, D, A = obs.shape[0], self.obs_dim, self.act_out
+        need = n * (D + A + 2) + A
+        blk = getattr(self, "_pin_block", None)
+        if blk is None or blk.numel() < need:
+            blk = self._pin_block = th.empty(max(need, 1024), dtype=th.float32).pin_memory()
+        o, off = blk[:n * D].view(n, D), n * D
+        head, off = blk[off:off + n * A].view(n, A), off + n * A
+        values, off = blk[off:off + n], off + n
+        cost_values, off = blk[off:off + n], off + n
+        log_std = blk[off:off + A]
+        o.copy_(obs)
+        cfg = getattr(self, "_fwd_cfg", None)          # (the forward reads the shape fields only: built once, ~15 us per make_cfg)
+        if cfg is None:
+            cfg = self._fwd_cfg = self.make_cfg()
+
+        def launch():
+            stream = th.cuda.current_stream()
+            _lib.check(_lib.lib().icrl_policy_forward(C.byref(cfg), _lib.ptr(self._params), _lib.ptr(o), n, _lib.ptr(head),
+                                                      _lib.ptr(values), _lib.ptr(cost_values), C.c_void_p(stream.cuda_stream)))
+            if not self.is_discrete:
+                log_std.copy_(self._params[:A], non_blocking=True)
+            stream.synchronize()
+
+        if th.cuda.current_device() == self.device.index:
+            launch()
+        else:
+            with th.cuda.device(self.device):
+                launch()
+        out = blk[n * D:n * (D + A + 2) + A].clone()    # one copy out of the staging block
+        head = out[:n * A].view(n, A)
+        return head, out[n * A:n * A + n], out[n * A + n:n * A + 2 * n], out[n * A + 2 * n:]
+
     def forward(self, obs: th.Tensor, deterministic: bool = False):
         """policies.py:716-731: actions, values, cost_values, log_prob.  Heads come from the CUDA forward; sampling uses
         the host torch generator exactly like the reference's CPU `Normal.rsample` / `Categorical.sample`, so a
         given torch seed produces the same exploration noise."""
-        head, values, cost_values = self.forward_heads(th.as_tensor(obs))
-        head = head.cpu()
+        obs = th.as_tensor(obs)
+        if not obs.is_cuda and obs.numel() <= 64 * self.obs_dim:
+            obs = obs.to(th.float32).reshape(-1, self.obs_dim)
+            head, values, cost_values, log_std = self._forward_heads_small(obs)
+        else:
+            head, values, cost_values = self.forward_heads(obs)
+            head, values, cost_values = head.cpu(), values.cpu(), cost_values.cpu()
+            log_std = None if self.is_discrete else self.log_std.cpu()
         if self.is_discrete:
             probs = th.softmax(head, dim=-1)
             actions = th.argmax(probs, dim=1) if deterministic else th.multinomial(probs, 1).squeeze(-1)
+            log_prob, _ = self._dist_terms(head, actions, log_std)
         else:
-            std = th.ones_like(head) * self.log_std.cpu().exp()
+            # the terms that depend on log_std only change with train(): cached per (log_std bytes, batch shape); the per-step
+            # expression below is the reference's, operation for operation (distributions.py:143-167 -> Normal.log_prob)
+            c = getattr(self, "_gauss_cache", None)
+            if c is None or c[1].shape != head.shape or not th.equal(c[0], log_std):
+                scale = th.ones_like(head) * log_std.exp()
+                c = self._gauss_cache = (log_std.clone(), scale, scale.log(), 2 * scale ** 2)
+            _, std, log_scale, two_var = c
             actions = head if deterministic else head + std * th.empty_like(head).normal_()
-        log_prob, _ = self._dist_terms(head, actions)
-        return actions, values.cpu().reshape(-1, 1), cost_values.cpu().reshape(-1, 1), log_prob
+            log_prob = (-((actions - head) ** 2) / two_var - log_scale - math.log(math.sqrt(2 * math.pi))).sum(1)
+        return actions, values.reshape(-1, 1), cost_values.reshape(-1, 1), log_prob
 
     __call__ = forward
 

@@ -190,3 +190,26 @@ def test_policy_forward_vs_oracle():
         np.testing.assert_allclose(head.cpu().numpy(), wh.numpy(), rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(v.cpu().numpy(), wv.numpy().ravel(), rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(cv.cpu().numpy(), wcv.numpy().ravel(), rtol=1e-5, atol=1e-6)
+
+
+def test_rollout_time_forward_zero_copy_path_equals_staged_path():
+    """ActorTwoCriticsPolicy.forward on a handful of host rows (the per-environment-step call of collect_rollouts) reads them
+    from, and writes heads / values to, a host-mapped pinned block with cached log_std terms; a CUDA input takes the staged
+    path with blocking downloads.  Same torch seed -> identical actions, values and log-probs (also after a parameter change)."""
+    for case in ("hc", "lgw"):
+        d = load_golden(f"k4_{case}")
+        algo, hp, names = build_algo(d)
+        pol = algo.policy
+        obs = th.tensor(d["buf.observations"].reshape(-1, d["buf.observations"].shape[-1])[:5].copy())
+        for rep in range(2):
+            th.manual_seed(11 + rep)
+            small = pol.forward(obs)
+            th.manual_seed(11 + rep)
+            staged = pol.forward(obs.cuda())
+            for a, b in zip(small, staged):
+                assert a.device.type == "cpu" and b.device.type == "cpu"
+                assert th.equal(a, b), case
+            det = pol.forward(obs, deterministic=True)
+            assert th.equal(det[0], pol.forward(obs.cuda(), deterministic=True)[0])
+            if not pol.is_discrete:           # move log_std: the cached terms must follow
+                pol._params[:pol.act_out] += 0.25
