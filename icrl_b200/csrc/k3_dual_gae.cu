@@ -16,6 +16,9 @@
 // row access of a lane group is one full 32-byte sector) for wide buffers, 4 for narrow ones (twice the time slots per CTA).
 #include <stdlib.h>
 
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace icrl {
@@ -230,9 +233,39 @@ int icrl_dual_gae_host(const float* rewards, const float* reward_values, const f
     // one staging buffer: 5 inputs [T,E] + 2 [E] + last_dones | 4 outputs [T,E]
     const size_t in_bytes = (5 * n + 2 * (size_t)E) * 4 + (size_t)E, out_bytes = 4 * n * 4;
     void *din, *dout;
-    if ((rc = icrl::device_scratch(icrl::SLOT_IN0, in_bytes, &din))) return rc;
-    if ((rc = icrl::device_scratch(icrl::SLOT_OUT0, out_bytes, &dout))) return rc;
+    // rollout-sized buffers (2048 x 5 in every shipped config): the kernel reads every input once and writes every output
+    // once, so it works straight on a host-mapped pinned block (UVA) -- one launch + one synchronisation instead of eight
+    // staged H2D copies, the launch, four D2H copies and the synchronisation
+    const bool zero_copy = in_bytes + out_bytes <= (1u << 20) && getenv("ICRL_K3_NO_ZEROCOPY") == nullptr;
+    if (zero_copy) {
+        const size_t in_al = (in_bytes + 15) / 16 * 16;
+        void* pin;
+        if ((rc = icrl::pinned_scratch(icrl::SLOT_WORK0, in_al + out_bytes, &pin))) return rc;
+        din = pin;
+        dout = static_cast<unsigned char*>(pin) + in_al;
+    } else {
+        if ((rc = icrl::device_scratch(icrl::SLOT_IN0, in_bytes, &din))) return rc;
+        if ((rc = icrl::device_scratch(icrl::SLOT_OUT0, out_bytes, &dout))) return rc;
+    }
     float* f = (float*)din;
+    if (zero_copy) {
+        const float* hin0[5] = {rewards, reward_values, costs, cost_values, dones};
+        for (int i = 0; i < 5; ++i) memcpy(f + i * n, hin0[i], n * 4);
+        memcpy(f + 5 * n, reward_last_value, (size_t)E * 4);
+        memcpy(f + 5 * n + E, cost_last_value, (size_t)E * 4);
+        memcpy(f + 5 * n + 2 * (size_t)E, last_dones, (size_t)E);
+        a.r = f; a.vr = f + n; a.c = f + 2 * n; a.vc = f + 3 * n; a.dones = f + 4 * n;
+        a.last_vr = f + 5 * n;
+        a.last_vc = f + 5 * n + E;
+        a.last_dones = (const uint8_t*)(f + 5 * n + 2 * (size_t)E);
+        float* o = (float*)dout;
+        a.adv_r = o; a.ret_r = o + n; a.adv_c = o + 2 * n; a.ret_c = o + 3 * n;
+        if ((rc = icrl::dual_gae_device(a, st))) return rc;
+        ICRL_CUDA(cudaStreamSynchronize(st));
+        float* hout0[4] = {reward_advantages, reward_returns, cost_advantages, cost_returns};
+        for (int i = 0; i < 4; ++i) memcpy(hout0[i], o + i * n, n * 4);
+        return 0;
+    }
     const float* hin[5] = {rewards, reward_values, costs, cost_values, dones};
     const float** dev_in[5] = {&a.r, &a.vr, &a.c, &a.vc, &a.dones};
     for (int i = 0; i < 5; ++i) {
