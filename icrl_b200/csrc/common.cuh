@@ -43,7 +43,7 @@ int sm_count();
 
 // grow-only device / pinned-host scratch, one slot per purpose (not thread safe: the learner is single threaded,
 // as the reference's is -- SURVEY §8b "Threading").
-enum Slot { SLOT_IN0 = 0, SLOT_IN1, SLOT_OUT0, SLOT_WORK0, SLOT_WORK1, SLOT_WORK2, SLOT_WORK3, SLOT_WORK4, SLOT_WORK5, SLOT_PPO0, SLOT_PPO1, SLOT_PPO2, SLOT_PPO3, SLOT_PPO4, SLOT_PPO5, SLOT_COUNT };
+enum Slot { SLOT_IN0 = 0, SLOT_IN1, SLOT_OUT0, SLOT_WORK0, SLOT_WORK1, SLOT_WORK2, SLOT_WORK3, SLOT_WORK4, SLOT_WORK5, SLOT_PPO0, SLOT_PPO1, SLOT_PPO2, SLOT_PPO3, SLOT_PPO4, SLOT_PPO5, SLOT_K5, SLOT_COUNT };
 int device_scratch(Slot s, size_t bytes, void** ptr);
 int pinned_scratch(Slot s, size_t bytes, void** ptr);
 

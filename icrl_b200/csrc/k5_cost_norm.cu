@@ -157,7 +157,7 @@ __device__ __forceinline__ double k5_div(double a, double b, double r) {
 __global__ void __launch_bounds__(K5_THREADS) cost_norm_fused_kernel(
         const float* __restrict__ orig_costs, const float* __restrict__ dones, const uint8_t* __restrict__ last_dones, int T,
         int E, int TT, double gamma, double epsilon, double clip, int norm_cost, int fastdiv, double* __restrict__ state,
-        float* __restrict__ costs, long long* __restrict__ prof) {
+        float* __restrict__ costs, double* __restrict__ var_out, long long* __restrict__ prof) {
     extern __shared__ __align__(16) unsigned char k5_smem[];
     double* RET = reinterpret_cast<double*>(k5_smem);
     double* BM = RET + (size_t)TT * E;
@@ -346,14 +346,20 @@ __global__ void __launch_bounds__(K5_THREADS) cost_norm_fused_kernel(
         if (prof && (tid == 0 || tid == 96 || tid == 32)) atomicAdd((unsigned long long*)&prof[tid == 0 ? 4 : tid == 96 ? 5 : 7], (unsigned long long)(clock64() - tc0));
         __syncthreads();
         K5_MARK(3)
-        // ---- normalise (a separate per-step square-root pass was measured 5x slower than recomputing it per element)
-        for (int i = tid; i < tt * E; i += K5_THREADS) {
-            float c = Cs[i];
-            if (norm_cost) {
-                const double x = __ddiv_rn((double)c, __dsqrt_rn(__dadd_rn(VT[i / E], epsilon)));
-                c = (float)fmin(fmax(x, -clip), clip);
+        // ---- the normalisation itself (a float64 division and square root per element) runs on the whole GPU afterwards
+        // (cost_apply_kernel): in this single CTA it was 85 k of the kernel's 440 k cycles -- one SM's FP64 pipe -- and letting
+        // half of the CTA trail the variance chain only slowed the chains down (they share that pipe: 239 -> 254 us).
+        if (var_out != nullptr) {
+            for (int i = tid; i < tt; i += K5_THREADS) var_out[t0 + i] = VT[i];
+        } else {
+            for (int i = tid; i < tt * E; i += K5_THREADS) {
+                float c = Cs[i];
+                if (norm_cost) {
+                    const double x = __ddiv_rn((double)c, __dsqrt_rn(__dadd_rn(VT[i / E], epsilon)));
+                    c = (float)fmin(fmax(x, -clip), clip);
+                }
+                costs[(size_t)t0 * E + i] = c;
             }
-            costs[(size_t)t0 * E + i] = c;
         }
         __syncthreads();
         K5_MARK(6)
@@ -395,9 +401,17 @@ extern "C" int icrl_cost_normalize(const float* orig_costs, const float* dones, 
         if (timing)
             if (int rc = device_scratch(SLOT_WORK3, 64, (void**)&prof)) return rc;
         if (prof) ICRL_CUDA(cudaMemsetAsync(prof, 0, 64, st));
+        double* var_t = nullptr;                    // running variance after every step, for the grid-wide normalisation pass
+        if (norm_cost)
+            if (int rc = device_scratch(SLOT_K5, (size_t)T * sizeof(double), (void**)&var_t)) return rc;
         cost_norm_fused_kernel<<<1, K5_THREADS, smem, st>>>(orig_costs, dones, last_dones, T, E, TT, cost_gamma, epsilon,
-                                                            clip_cost, norm_cost, fastdiv, state, costs, prof);
+                                                            clip_cost, norm_cost, fastdiv, state, costs, var_t, prof);
         ICRL_LAUNCH_CHECK();
+        if (norm_cost) {
+            const int blocks = (int)((total + 255) / 256 < (long long)sm_count() * 8 ? (total + 255) / 256 : (long long)sm_count() * 8);
+            cost_apply_kernel<<<blocks, 256, 0, st>>>(orig_costs, var_t, state, 1, total, E, epsilon, clip_cost, costs);
+            ICRL_LAUNCH_CHECK();
+        }
         if (prof) {   // ICRL_K5_TIMING=1: per-phase cycles of thread 0 (load, return chain, moments, Chan chain, apply)
             long long h[8];
             ICRL_CUDA(cudaStreamSynchronize(st));
