@@ -83,7 +83,10 @@ int64_t icrl_cn_param_count(const icrl_cn_desc* d);
  * out[n_rows] = 1 - zeta(x) when out_kind == 0 (cost), zeta(x) when out_kind == 1 (prediction). */
 int icrl_cn_forward(const icrl_cn_desc* d, const void* obs, int32_t obs_is_f64, const float* acs,
                     int64_t n_rows, float* out, int32_t out_kind, void* stream);
-/* same with HOST buffers (obs, acs, out); synchronous. */
+/* same with HOST buffers (obs, acs, out); synchronous.  This is the per-environment-step call of
+ * VecCostWrapper.step_wait (vec_cost_wrapper.py:62): batches of up to 64 KB are copied into one host-mapped pinned block that
+ * the kernel reads and writes directly (one launch + one synchronisation; <= 16 rows run a CTA-per-row kernel); larger batches
+ * are staged through device scratch. */
 int icrl_cn_forward_host(const icrl_cn_desc* d, const void* obs, int32_t obs_is_f64, const float* acs,
                          int64_t n_rows, float* out, int32_t out_kind, void* stream);
 
@@ -165,7 +168,7 @@ int icrl_dual_gae(const float* rewards, const float* reward_values, const float*
                   double reward_gamma, double reward_gae_lambda, double cost_gamma, double cost_gae_lambda,
                   float* reward_advantages, float* reward_returns, float* cost_advantages, float* cost_returns,
                   void* stream);
-/* HOST buffers; synchronous. */
+/* HOST buffers; synchronous (rollout-sized buffers, <= 1 MB in total, run on a host-mapped pinned block). */
 int icrl_dual_gae_host(const float* rewards, const float* reward_values, const float* costs, const float* cost_values,
                        const float* dones, const float* reward_last_value, const float* cost_last_value,
                        const uint8_t* last_dones, int32_t T, int32_t E,
