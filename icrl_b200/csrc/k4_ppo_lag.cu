@@ -273,7 +273,7 @@ struct TimingCounters<false> {
 // gradients meet in global memory (L2): write -> grid barrier -> each (cluster, half) sums its few floats over all clusters in
 // cluster order (and, data parallel, exchanges that slice with the peer GPUs' same reducer over NVLink) -> grid barrier ->
 // everybody reads the totals.  All replicas then apply the identical clip + Adam update, so they never diverge.
-template <int NT1, bool DIST, bool WIDE>
+template <int NT1, bool DIST, bool WIDE, bool TIMED>
 #ifdef ICRL_K4_MAXREG       // A/B builds (tools/build_variants.sh): an explicit register cap instead of the launch bounds
 #define ICRL_K4_BOUNDS __maxnreg__(ICRL_K4_MAXREG)
 #else
@@ -457,15 +457,17 @@ __global__ void ICRL_K4_BOUNDS ppo_train_kernel(const __grid_constant__ PpoArgs 
     bool kl_stopped = false;
     double epoch_kl_sum = 0.0;
     bool stop_all = false;
-    const bool timed = (a.timing != nullptr) && tid == 0 && working && cluster_id == 0;
+    // TIMED = false (every launch unless ICRL_PPO_TIMING is set): the per-phase counters and their marks are compiled out --
+    // measured 1.3 % (HalfCheetah) to 4.7 % (AntWall) per optimiser step against a run-time `if (timed)` around every mark
+    const bool timed = TIMED && (a.timing != nullptr) && tid == 0 && working && cluster_id == 0;
     long long tmark = clock64();
     // per-phase cycle counters of thread 0 (ICRL_PPO_TIMING).  Measured (profiles/k4_variants_r02.txt): the wide dW1 tiles
     // (NT1 >= 4, AntWall) have no registers to spare -- keeping the 20 counters in shared memory takes 21.5 -> 19.5 us per
     // optimiser step there -- while the HalfCheetah instantiation is 2 % faster with them in registers.
     TimingCounters<(NT1 <= 2)> tacc;
-    tacc.init(sm + L.tacc, timed);
+    if (TIMED) tacc.init(sm + L.tacc, timed);
 #define ICRL_MARK(i)                                   \
-    if (timed) {                                       \
+    if (TIMED && timed) {                              \
         const long long now__ = clock64();             \
         tacc[i] += (unsigned long long)(now__ - tmark); \
         tmark = now__;                                 \
@@ -1572,8 +1574,13 @@ __global__ void ICRL_K4_BOUNDS ppo_train_kernel(const __grid_constant__ PpoArgs 
 template <int NT1, bool WIDE>
 static int launch_cfg(const PpoArgs& a, cudaStream_t st, int n_clusters, cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr,
                       void (**kern_out)(const PpoArgs)) {
-    void (*kern)(const PpoArgs) = WIDE ? (a.world > 1 ? ppo_train_kernel<NT1, true, true> : ppo_train_kernel<NT1, false, true>)
-                                       : (a.world > 1 ? ppo_train_kernel<NT1, true, false> : ppo_train_kernel<NT1, false, false>);
+    void (*kern)(const PpoArgs);
+    if (a.timing != nullptr)
+        kern = WIDE ? (a.world > 1 ? ppo_train_kernel<NT1, true, true, true> : ppo_train_kernel<NT1, false, true, true>)
+                    : (a.world > 1 ? ppo_train_kernel<NT1, true, false, true> : ppo_train_kernel<NT1, false, false, true>);
+    else
+        kern = WIDE ? (a.world > 1 ? ppo_train_kernel<NT1, true, true, false> : ppo_train_kernel<NT1, false, true, false>)
+                    : (a.world > 1 ? ppo_train_kernel<NT1, true, false, false> : ppo_train_kernel<NT1, false, false, false>);
     const PpoSmem L = ppo_smem_layout(a.DP, ppo_pay_floats<NT1>());
     if (L.total_bytes > 227 * 1024) {
         set_error("obs_dim %d needs %d bytes of shared memory (> 227 KB)", a.D, L.total_bytes);
