@@ -37,7 +37,9 @@ def _digest():
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
-    stamp = os.path.join(OBJ, "stamp")
+    # the stamp sits NEXT TO the library (git-ignored, but it travels to the GPU box with the snapshot, unlike build/): a box
+    # that received an up-to-date .so does not recompile (k4_ppo_lag.cu alone takes ~2 minutes)
+    stamp = LIB + ".stamp"
     digest = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
         return LIB
