@@ -150,3 +150,34 @@ def test_sharded_constraint_net_update_gloo_world2(tmp_path):
                         "127.0.0.1", "--master-port", "29534", str(script)], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_bench_replica_digest_gloo_world2(tmp_path):
+    """bench.py's post-run soak check: `replicas_identical` is true only if every rank holds bit-identical tensors (a one-ulp
+    difference in one element on one rank, or two swapped elements, must be caught)."""
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent('''
+        import os, sys, torch as th, torch.distributed as dist
+        sys.path.insert(0, %r)
+        import bench
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        th.manual_seed(0)
+        a, b = th.randn(1000), th.randn(37, 3)
+        assert bench.replicas_identical([a, b], world)
+        a2 = a.clone()
+        if rank == 1:
+            a2[123] = th.nextafter(a2[123], th.tensor(float("inf")))
+        assert not bench.replicas_identical([a2, b], world)
+        a3 = a.clone()
+        if rank == 0:
+            a3[[5, 6]] = a3[[6, 5]]
+        assert not bench.replicas_identical([a3, b], world)
+        dist.destroy_process_group()
+        print("ok", rank)
+    ''' % ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29534", str(script)], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2
