@@ -229,6 +229,9 @@ class PPOLagrangian:
         """While the kernel runs the host is idle: draw the next train()'s permutations from the state the global numpy RNG
         will be in if (a) no epoch is cut by target_kl and (b) nobody touches np.random before the next call.  The next
         call uses them only if the RNG state it finds is exactly that one -- the stream the reference would see is unchanged."""
+        if n * self.n_epochs > (1 << 22):       # large buffers: the draw outlasts the kernel and would double the host memory
+            self._spec_perms = None
+            return
         np.random.set_state(state_if_all_epochs_run)
         perms, states = self._draw_permutations(n)
         self._spec_perms = (n, self.n_epochs, state_if_all_epochs_run, perms, states)
